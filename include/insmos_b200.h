@@ -1,0 +1,234 @@
+/*
+ * insmos_b200.h -- C ABI of libinsmos_b200.so
+ *
+ * B200-native (sm_100a) kernels for the sparse-voxel forward path of InsMOS
+ * (SURVEY.md section 8).  This is the drop-in boundary: plain pointers and sizes,
+ * no torch / ATen / pybind types.  Every pointer marked [dev] is a device
+ * pointer owned by the caller (the Python host side allocates through the
+ * PyTorch caching allocator); `stream` is a cudaStream_t passed as void*.
+ * Every entry point returns 0 on success or a negative INSMOS_ERR_* code; none
+ * of them exits the process or throws (the reference's native code calls
+ * exit(-1) on error: models/bbox_post_process/src/iou3d_nms.cpp:14-38).
+ * No entry point synchronises the stream; data-dependent sizes are written to
+ * small [dev] counter arrays that the caller reads back when it needs them.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository):
+ *   - MinkowskiEngine (external, un-vendored): ME.utils.sparse_collate,
+ *     ME.TensorField(...).sparse(), SparseTensor.slice, MinkowskiConvolution,
+ *     MinkowskiConvolutionTranspose, MinkowskiBatchNorm, MinkowskiReLU, ME.cat
+ *     -- call sites models/backbones_3d/motionnet.py:21-50,
+ *        models/MinkowskiEngine/minkunet.py:52-181, resnet.py:87-126
+ *   - spconv 2.3.6 (external): PointToVoxel.generate_voxel_with_id,
+ *     SparseConvTensor(.dense), SubMConv3d, SparseConv3d, SparseInverseConv3d,
+ *     gather_features_by_pc_voxel_id
+ *     -- call sites models/backbones_3d/voxel_generate.py:17-31,
+ *        models/backbones_3d/spconv_unet.py:120-208,284-410
+ *   - iou3d_nms_cuda.nms_gpu  (models/bbox_post_process/src/iou3d_nms.cpp:90-136,
+ *     iou3d_nms_kernel.cu:267-311)
+ *   - Array_Index.find_features_by_bbox_with_yaw (models/utils/src/Array_Index.cpp:14-79)
+ *   - CenterHead.generate_predicted_boxes (models/backbones_2d/center_head.py:251-276)
+ *     + sigmoid/max of post_processing (models/post_process.py:146-192)
+ */
+#ifndef INSMOS_B200_H
+#define INSMOS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define INSMOS_OK                 0
+#define INSMOS_ERR_INVALID_ARG   -1
+#define INSMOS_ERR_CUDA          -2
+#define INSMOS_ERR_UNSUPPORTED   -3
+
+/* bits of the device-side error word (counters[INSMOS_CNT_ERR]) */
+#define INSMOS_DEVERR_COORD_RANGE  1   /* coordinate does not fit the 64-bit key packing */
+#define INSMOS_DEVERR_ROW_RANGE    2   /* row index does not fit 25 bits of a rule-book entry */
+
+/* layout of the int32 counter arrays written by the coordinate ops */
+#define INSMOS_CNT_ROWS   0   /* number of unique rows / voxels produced            */
+#define INSMOS_CNT_AUX    1   /* op specific (voxelize4d: number of t==0 points)   */
+#define INSMOS_CNT_ERR    2   /* INSMOS_DEVERR_* bits                              */
+#define INSMOS_CNT_TOTAL  3   /* op specific (voxelize3d: distinct voxels before the cap) */
+#define INSMOS_NUM_COUNTERS 4
+
+/* One slot of the coordinate hash table: 16 bytes.
+ *   key   packed (batch,c0,c1,c2,c3); all-ones = empty
+ *   first smallest input index that produced the key (defines first-occurrence order)
+ *   row   output row id (-1 while unassigned / dropped by a cap)                     */
+typedef struct {
+    uint64_t key;
+    int32_t  first;
+    int32_t  row;
+} insmos_slot_t;
+
+/* Rule-book geometry: how the input coordinate probed for (output row, kernel offset k)
+ * is derived.  Coordinates are rows of int32 [ncol] = (batch, c0..c{ndim-1}).
+ * mode 0 (affine): in[d] = (out[d]*a[d] + b[d] + k_d*e[d]) / q[d]   (must divide exactly)
+ * mode 1 (ME transposed, kernel 2 stride 2): in[d] = floor(out[d]/up_q[d])*up_q[d]; the pair
+ *        exists only for the k whose digits equal (out[d]-in[d])/up_ts[d].
+ * k digits: k = sum_d k_d * prod_{d' before d} ksize[d'], dimension 0 fastest when
+ * first_fastest != 0 (MinkowskiEngine), last dimension fastest otherwise (spconv zyx). */
+typedef struct {
+    int32_t mode;
+    int32_t ncol;
+    int32_t ndim;
+    int32_t first_fastest;
+    int32_t K;
+    int32_t ksize[4];
+    int32_t a[4];
+    int32_t b[4];
+    int32_t e[4];
+    int32_t q[4];
+    int32_t up_q[4];
+    int32_t up_ts[4];
+} insmos_mapspec_t;
+
+/* Epilogue fused into convolution / linear kernels:
+ *   v = acc; v = v*scale[c] + shift[c] (if scale) ; v += bias[c] (if bias) ;
+ *   v += residual[row,c] (if residual) ; v = max(v,0) (if relu)                      */
+typedef struct {
+    const float* scale;     /* [dev] [Cout] or NULL */
+    const float* shift;     /* [dev] [Cout] or NULL (required when scale given) */
+    const float* bias;      /* [dev] [Cout] or NULL */
+    const float* residual;  /* [dev] [N_out, Cout] or NULL */
+    int32_t relu;
+} insmos_epilogue_t;
+
+const char* insmos_version(void);
+const char* insmos_last_error(void);          /* text of the last CUDA error seen by this thread */
+int64_t insmos_hash_capacity(int64_t n);      /* power of two >= 2n (min 1024) */
+int64_t insmos_scan_scratch_bytes(int64_t n); /* scratch needed by ops that scan n elements */
+
+/* ---- coordinate ops ---------------------------------------------------------------------- */
+
+int insmos_table_clear(insmos_slot_t* table, int64_t cap, void* stream);
+
+/* a1+a2 (motionnet.py:22-36): fused quantise (fp32 true division, floor) + unique.
+ * points [n, point_stride] f32 rows (x,y,z,intensity,t); quant = (vx,vy,vz,dt) host array.
+ * Outputs: out_coords [<=n,5] i32 (0,x,y,z,t) in first-occurrence order, inverse [n] i32
+ * (point -> voxel row, -1 on range error), cur_index [<=n] i32 = ascending indices of the points
+ * whose t/dt == 0 (motionnet.py:42), counters[ROWS]=#voxels, counters[AUX]=#current points. */
+int insmos_voxelize4d(const float* points, int64_t n, int32_t point_stride, const float* quant,
+                      insmos_slot_t* table, int64_t cap, int32_t* slot_of_point,
+                      int32_t* out_coords, int32_t* inverse, int32_t* cur_index,
+                      int32_t* counters, void* scratch, void* stream);
+
+/* unique rows of int32 coords [n,ncol] in first-occurrence order (ME TensorField.sparse on
+ * already-floored coordinates; ME coordinate-manager stride when q given: dims are floored to
+ * multiples of q[d] first).  q = host array [ncol-1] or NULL. */
+int insmos_unique_coords(const int32_t* coords, int64_t n, int32_t ncol, const int32_t* q,
+                         insmos_slot_t* table, int64_t cap, int32_t* slot_of_point,
+                         int32_t* out_coords, int32_t* inverse,
+                         int32_t* counters, void* scratch, void* stream);
+
+/* spconv SparseConv3d output coordinate generation (oracle order: input rows ascending,
+ * kernel offsets ascending, first occurrence).  in_coords [n,4] (b,z,y,x). */
+int64_t insmos_spconv_out_scratch_bytes(int64_t n, int32_t K);   /* size of `scratch` below */
+int insmos_spconv_out_coords(const int32_t* in_coords, int64_t n,
+                             const int32_t* ksize, const int32_t* stride, const int32_t* pad,
+                             const int32_t* out_shape,
+                             insmos_slot_t* table, int64_t cap,
+                             int32_t* out_coords, int32_t* counters, void* scratch, void* stream);
+
+/* a6+a7 (voxel_generate.py:17-31, mean_vfe.py:47-52): capped hard voxelisation with ids +
+ * fused per-voxel mean.  points [n,C] f32 (first three columns x,y,z); range = (xmin,ymin,zmin,
+ * xmax,ymax,zmax), vsize = (vx,vy,vz), grid = (gx,gy,gz) host arrays.
+ * Outputs: coords [<=max_voxels,4] i32 (0,z,y,x), num_points [<=max_voxels] i32,
+ * voxels [<=max_voxels,max_points,C] f32 zero padded (may be NULL), mean [<=max_voxels,C] f32,
+ * pc_voxel_id [n] i32 (-1 dropped). work = [max_voxels*(1+max_points)] i32 scratch. */
+int insmos_voxelize3d(const float* points, int64_t n, int32_t C,
+                      const float* range, const float* vsize, const int32_t* grid,
+                      int32_t max_voxels, int32_t max_points,
+                      insmos_slot_t* table, int64_t cap, int32_t* slot_of_point,
+                      int32_t* coords, int32_t* num_points, float* voxels, float* mean,
+                      int32_t* pc_voxel_id, int32_t* work,
+                      int32_t* counters, void* scratch, void* stream);
+
+/* ---- rule books --------------------------------------------------------------------------- */
+
+/* Output-stationary, tiled, k-bucketed rule book (a4 + spconv indice pairs):
+ * output rows are cut into tiles of TM rows; tile t owns entries[t*TM*K .. ) ; seg[t*(K+1)+k]
+ * (uint16) = start of offset k's bucket inside the tile; entry = (out_row_in_tile << 25) | in_row.
+ * pair_count[0] (uint64, [dev]) accumulates the number of pairs. */
+int64_t insmos_rulebook_entries_capacity(int64_t n_out, int32_t K, int32_t TM);
+int insmos_rulebook_build(const int32_t* out_coords, int64_t n_out,
+                          const insmos_slot_t* in_table, int64_t in_cap,
+                          const insmos_mapspec_t* spec, int32_t TM,
+                          uint16_t* seg, uint32_t* entries, unsigned long long* pair_count,
+                          int32_t* counters, void* stream);
+
+/* ---- feature ops -------------------------------------------------------------------------- */
+
+/* sparse convolution forward over a tiled rule book (a3, a8, a12).
+ * in [n_in,Cin] f32, weight [K,Cin,Cout] f32, out [n_out,Cout] f32.
+ * algo: 0 = auto, 1 = SIMT fp32, 2 = tensor-core 3xTF32 (mma.sync m16n8k8, fp32 accumulate). */
+int insmos_sparse_conv_fwd(const float* in, int64_t n_in, int32_t Cin,
+                           const float* weight, int32_t K, int32_t Cout,
+                           const uint16_t* seg, const uint32_t* entries, int32_t TM,
+                           float* out, int64_t n_out,
+                           const insmos_epilogue_t* ep, int32_t algo, void* stream);
+
+/* out[n,Cout] = in[n,Cin] . weight[Cin,Cout] + epilogue (ME kernel_size==1 conv, nn.Linear) */
+int insmos_linear_fwd(const float* in, int64_t n, int32_t Cin, const float* weight, int32_t Cout,
+                      float* out, const insmos_epilogue_t* ep, void* stream);
+
+/* elementwise epilogue alone on x [n,C] (MinkowskiBatchNorm eval, ReLU, residual add) */
+int insmos_affine_act(const float* x, int64_t n, int32_t C, float* out,
+                      const insmos_epilogue_t* ep, void* stream);
+
+/* out[n,C1+C2] = cat(a[n,C1], b[n,C2]) (ME.cat, torch.cat on features) */
+int insmos_concat2(const float* a, int32_t C1, const float* b, int32_t C2, int64_t n,
+                   float* out, void* stream);
+
+/* out[n,C] = a[n,C] + view(b[n,2C], n,C,2).sum(2)   (spconv_unet.py:213-238) ; a may be NULL */
+int insmos_pairsum_add(const float* a, const float* b, int64_t n, int32_t C, float* out, void* stream);
+
+/* out[i,:] = idx[i] >= 0 ? src[idx[i],:] : 0   (SparseTensor.slice, gather_features_by_pc_voxel_id) */
+int insmos_gather_rows(const float* src, int32_t C, const int32_t* idx, int64_t n, float* out, void* stream);
+
+/* per-voxel unweighted average of point features (ME TensorField.sparse default quantisation) */
+int insmos_segment_mean(const float* feat, int32_t C, const int32_t* inverse, int64_t n,
+                        float* out, int32_t* cnt, int64_t n_rows, void* stream);
+
+/* a5 (motionnet.py:42-48): out[j,0:4] = points[cur_index[j],0:4]; out[j,4:4+Cm] = vox_feat[inverse[cur_index[j]],0:Cm] */
+int insmos_build_current_points(const float* points, int32_t point_stride, const int32_t* cur_index,
+                                int64_t n_cur, const int32_t* inverse, const float* vox_feat, int32_t Cfeat,
+                                int32_t Cm, float* out, void* stream);
+
+/* SparseConvTensor.dense() for batch 1: out[C,D,H,W] (pre-zeroed by the callee) ; coords [n,4] (b,z,y,x) */
+int insmos_dense_scatter(const float* feat, const int32_t* coords, int64_t n, int32_t C,
+                         int32_t D, int32_t H, int32_t W, float* out, void* stream);
+
+/* ---- detection head ----------------------------------------------------------------------- */
+
+/* CenterHead decode + sigmoid/max (center_head.py:251-276, post_process.py:146-192).
+ * cls [ncls,H,W], box [8,H,W] (NCHW conv outputs, batch 1).  boxes [H*W,7], scores [H*W], labels [H*W] (1-based). */
+int insmos_center_decode(const float* cls, const float* box, int32_t ncls, int32_t H, int32_t W,
+                         float out_size_factor, float vx, float vy, float x_min, float y_min,
+                         float* boxes, float* scores, int32_t* labels, void* stream);
+
+/* rotated BEV NMS on boxes [n,7] already sorted by descending score (nms_gpu).
+ * mask = [n*ceil(n/64)] uint64 scratch. keep [<=max_keep] i32 ascending, num_keep [1] i32. */
+int insmos_nms_rotated(const float* boxes, int32_t n, float thresh, int32_t max_keep,
+                       unsigned long long* mask, int32_t* keep, int32_t* num_keep, void* stream);
+
+/* boxes7 [nb,7] metric (x,y,z,dx,dy,dz,yaw) + labels [nb] -> boxes8 [nb,8] in voxel units of the
+ * stride-`stride` level (spconv_unet.py:321-330), fp32 op order preserved. */
+int insmos_boxes_to_voxel_units(const float* boxes7, const int32_t* labels, int32_t nb,
+                                const float* range_min, const float* vsize, float stride,
+                                float* boxes8, void* stream);
+
+/* Array_Index.find_features_by_bbox_with_yaw on device, including its first-hit pruning quirk.
+ * coords [n,4] (b,z,y,x) i32; boxes8 [nb,8] (cx,cy,cz,dx,dy,dz,yaw,label) scaled by `mult`
+ * (exact power of two, spconv_unet.py:358,373,388). out[j*out_stride + label-1] = 1.0f for hits
+ * (caller zero-initialises). first_hit [nb] i32 scratch. */
+int insmos_box_membership(const int32_t* coords, int64_t n, const float* boxes8, int32_t nb, float mult,
+                          float* out, int32_t out_stride, int32_t* first_hit, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INSMOS_B200_H */

@@ -1,0 +1,398 @@
+// Feature kernels: sparse convolution over the tiled rule book (a3, a8, a12), 1x1 conv / linear,
+// fused BN(eval)+residual+ReLU epilogues, concat, pair-sum, gathers, dense scatter.
+//
+// Sparse convolution is output-stationary: a tile of TM output rows is accumulated in shared
+// memory, bucket by bucket (kernel offset k).  Inside one bucket every output row appears at most
+// once, so accumulation is a plain read-modify-write (shared-memory fp32 atomics are CAS loops on
+// sm_100a and are avoided).  Each output row is written to HBM exactly once, with the epilogue
+// (folded BatchNorm, residual, ReLU) applied in registers on the way out; every feature row is
+// gathered from L2, the 4-byte rule-book entries are streamed once.
+//
+// Two contraction paths:
+//   algo 1  SIMT fp32 FFMA, any Cin/Cout (reference path, also used for Cin < 8).
+//   algo 2  tensor cores: the pairs of one bucket are packed 16 at a time into the M dimension of
+//           mma.sync.m16n8k8 (100% useful rows, unlike a zero-padded output-stationary tile), the
+//           [Cin x Cout] weight slice of offset k is the B operand.  fp32 parity (logits within
+//           1e-3) rules out plain TF32, so every product is done as 3xTF32 (hi*hi + hi*lo + lo*hi,
+//           fp32 accumulate), which is fp32-accurate to ~2^-22.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float apply_epilogue(float v, int c, int64_t row, int Cout, const insmos_epilogue_t& ep) {
+    if (ep.scale) v = __fmaf_rn(v, __ldg(ep.scale + c), __ldg(ep.shift + c));
+    if (ep.bias) v += __ldg(ep.bias + c);
+    if (ep.residual) v += __ldg(ep.residual + row * Cout + c);
+    if (ep.relu) v = fmaxf(v, 0.0f);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// algo 1: SIMT
+#define SIMT_THREADS 256
+__global__ void __launch_bounds__(SIMT_THREADS)
+k_spconv_simt(const float* __restrict__ in, const float* __restrict__ W,
+              const uint16_t* __restrict__ seg, const uint32_t* __restrict__ entries,
+              float* __restrict__ out, int64_t n_out, int Cin, int Cout, int K, int TM, insmos_epilogue_t ep) {
+    extern __shared__ float sm[];
+    float* acc = sm;                                  // [TM*Cout]
+    int* sseg = reinterpret_cast<int*>(acc + TM * Cout);   // [K+1]
+    const int tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const uint16_t* tseg = seg + tile * (K + 1);
+    for (int k = tid; k <= K; k += SIMT_THREADS) sseg[k] = tseg[k];
+    for (int i = tid; i < TM * Cout; i += SIMT_THREADS) acc[i] = 0.0f;
+    __syncthreads();
+    const uint32_t* tent = entries + tile * (int64_t)TM * K;
+    for (int k = 0; k < K; ++k) {
+        const int s0 = sseg[k], n = sseg[k + 1] - s0;
+        if (n == 0) continue;                          // uniform across the block
+        const float* Wk = W + (int64_t)k * Cin * Cout;
+        for (int idx = tid; idx < n * Cout; idx += SIMT_THREADS) {
+            const int p = idx / Cout, co = idx - p * Cout;
+            const uint32_t e = __ldg(tent + s0 + p);
+            const float* x = in + (int64_t)(e & INSMOS_ROW_MASK) * Cin;
+            float a = 0.0f;
+            for (int ci = 0; ci < Cin; ++ci) a = __fmaf_rn(__ldg(x + ci), __ldg(Wk + ci * Cout + co), a);
+            acc[(e >> INSMOS_ROW_BITS) * Cout + co] += a;
+        }
+        __syncthreads();
+    }
+    const int64_t row0 = tile * TM;
+    const int rows = (int)((n_out - row0) < TM ? (n_out - row0) : TM);
+    for (int i = tid; i < rows * Cout; i += SIMT_THREADS) {
+        const int r = i / Cout, c = i - r * Cout;
+        out[(row0 + r) * Cout + c] = apply_epilogue(acc[i], c, row0 + r, Cout, ep);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// algo 2: tensor cores, 3xTF32
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+#define MMA_WARPS 4
+// NT: n-tiles (8 output channels each) per warp; WN: warps sharing one tile along Cout.
+// A block of 4 warps processes 4/WN tiles; warps never synchronise with each other (each owns
+// disjoint accumulator columns).
+// Fragment mapping (g = lane>>2, t = lane&3): the contraction index is permuted so that one lane's
+// two k-slots (t, t+4) are the adjacent channels (2t, 2t+1) -> one 8-byte load per gathered row.
+template <int NT, int WN>
+__global__ void __launch_bounds__(MMA_WARPS * 32)
+k_spconv_mma(const float* __restrict__ in, const float* __restrict__ W,
+             const uint16_t* __restrict__ seg, const uint32_t* __restrict__ entries,
+             float* __restrict__ out, int64_t n_out, int64_t n_tiles, int Cin, int Cout, int K, int TM,
+             insmos_epilogue_t ep) {
+    constexpr int TPB = MMA_WARPS / WN;
+    constexpr int CP = WN * NT * 8;                    // padded Cout held in shared memory
+    extern __shared__ float sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int tib = warp / WN, wn = warp % WN;
+    const int64_t tile = (int64_t)blockIdx.x * TPB + tib;
+    if (tile >= n_tiles) return;                       // warps are independent: no block barrier below
+    float* acc = sm + (size_t)tib * TM * CP;           // [TM][CP]
+    int* sseg = reinterpret_cast<int*>(sm + (size_t)TPB * TM * CP) + warp * (K + 1);
+    const uint16_t* tseg = seg + tile * (K + 1);
+    for (int k = lane; k <= K; k += 32) sseg[k] = tseg[k];
+    const int cbase = wn * NT * 8;
+    for (int i = lane; i < TM * NT * 8; i += 32) acc[(i / (NT * 8)) * CP + cbase + (i % (NT * 8))] = 0.0f;
+    __syncwarp();
+    const uint32_t* tent = entries + tile * (int64_t)TM * K;
+    const int KS = (Cin + 7) >> 3;
+    const bool even = (Cin & 1) == 0;
+    for (int k = 0; k < K; ++k) {
+        const int s0 = sseg[k], n = sseg[k + 1] - s0;
+        if (n == 0) continue;
+        const float* Wk = W + (int64_t)k * Cin * Cout;
+        for (int c0 = 0; c0 < n; c0 += 16) {
+            const bool v_lo = (c0 + g) < n, v_hi = (c0 + g + 8) < n;
+            const uint32_t e_lo = v_lo ? __ldg(tent + s0 + c0 + g) : 0u;
+            const uint32_t e_hi = v_hi ? __ldg(tent + s0 + c0 + g + 8) : 0u;
+            const float* x_lo = in + (int64_t)(e_lo & INSMOS_ROW_MASK) * Cin;
+            const float* x_hi = in + (int64_t)(e_hi & INSMOS_ROW_MASK) * Cin;
+            float d[NT][4];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) { d[nt][0] = d[nt][1] = d[nt][2] = d[nt][3] = 0.0f; }
+            for (int ks = 0; ks < KS; ++ks) {
+                const int col = ks * 8 + 2 * t;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;     // (g,2t) (g+8,2t) (g,2t+1) (g+8,2t+1)
+                if (even) {
+                    if (col < Cin) {
+                        if (v_lo) { const float2 v = __ldg(reinterpret_cast<const float2*>(x_lo + col)); a0 = v.x; a2 = v.y; }
+                        if (v_hi) { const float2 v = __ldg(reinterpret_cast<const float2*>(x_hi + col)); a1 = v.x; a3 = v.y; }
+                    }
+                } else {
+                    if (col < Cin) { if (v_lo) a0 = __ldg(x_lo + col); if (v_hi) a1 = __ldg(x_hi + col); }
+                    if (col + 1 < Cin) { if (v_lo) a2 = __ldg(x_lo + col + 1); if (v_hi) a3 = __ldg(x_hi + col + 1); }
+                }
+                uint32_t ah[4], al[4];
+                split_tf32(a0, ah[0], al[0]); split_tf32(a1, ah[1], al[1]);
+                split_tf32(a2, ah[2], al[2]); split_tf32(a3, ah[3], al[3]);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const int nc = cbase + nt * 8 + g;
+                    float b0 = 0.f, b1 = 0.f;
+                    if (nc < Cout) {
+                        if (col < Cin) b0 = __ldg(Wk + col * Cout + nc);
+                        if (col + 1 < Cin) b1 = __ldg(Wk + (col + 1) * Cout + nc);
+                    }
+                    uint32_t bh0, bl0, bh1, bl1;
+                    split_tf32(b0, bh0, bl0); split_tf32(b1, bh1, bl1);
+                    mma_tf32(d[nt], al, bh0, bh1);
+                    mma_tf32(d[nt], ah, bl0, bl1);
+                    mma_tf32(d[nt], ah, bh0, bh1);
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const int cc = cbase + nt * 8 + 2 * t;
+                if (v_lo) {
+                    float2* p = reinterpret_cast<float2*>(acc + (e_lo >> INSMOS_ROW_BITS) * CP + cc);
+                    float2 v = *p; v.x += d[nt][0]; v.y += d[nt][1]; *p = v;
+                }
+                if (v_hi) {
+                    float2* p = reinterpret_cast<float2*>(acc + (e_hi >> INSMOS_ROW_BITS) * CP + cc);
+                    float2 v = *p; v.x += d[nt][2]; v.y += d[nt][3]; *p = v;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    const int64_t row0 = tile * TM;
+    const int rows = (int)((n_out - row0) < TM ? (n_out - row0) : TM);
+    constexpr int CW = NT * 8;
+    for (int i = lane; i < rows * CW; i += 32) {
+        const int r = i / CW, c = cbase + (i % CW);
+        if (c < Cout) out[(row0 + r) * Cout + c] = apply_epilogue(acc[r * CP + c], c, row0 + r, Cout, ep);
+    }
+}
+
+template <int NT, int WN>
+static int launch_mma(const float* in, const float* W, const uint16_t* seg, const uint32_t* entries, float* out,
+                      int64_t n_out, int Cin, int Cout, int K, int TM, const insmos_epilogue_t& ep, cudaStream_t st) {
+    constexpr int TPB = MMA_WARPS / WN;
+    constexpr int CP = WN * NT * 8;
+    const size_t smem = sizeof(float) * (size_t)TPB * TM * CP + sizeof(int) * (size_t)MMA_WARPS * (K + 1);
+    if (smem > 220 * 1024) return INSMOS_ERR_UNSUPPORTED;
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_spconv_mma<NT, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int64_t n_tiles = ceil_div64(n_out, TM);
+    k_spconv_mma<NT, WN><<<(unsigned)ceil_div64(n_tiles, TPB), MMA_WARPS * 32, smem, st>>>(
+        in, W, seg, entries, out, n_out, n_tiles, Cin, Cout, K, TM, ep);
+    INSMOS_CHECK_LAUNCH("k_spconv_mma");
+    return INSMOS_OK;
+}
+
+extern "C" int insmos_sparse_conv_fwd(const float* in, int64_t n_in, int32_t Cin,
+                                      const float* weight, int32_t K, int32_t Cout,
+                                      const uint16_t* seg, const uint32_t* entries, int32_t TM,
+                                      float* out, int64_t n_out,
+                                      const insmos_epilogue_t* ep_in, int32_t algo, void* stream) {
+    if (!in || !weight || !seg || !entries || !out || Cin <= 0 || Cout <= 0 || K <= 0 || n_out < 0 || n_in < 0)
+        return INSMOS_ERR_INVALID_ARG;
+    if (TM != 16 && TM != 32 && TM != 64 && TM != 128) return INSMOS_ERR_INVALID_ARG;
+    if (n_in > (int64_t)INSMOS_ROW_MASK + 1) return INSMOS_ERR_UNSUPPORTED;
+    insmos_epilogue_t ep = {nullptr, nullptr, nullptr, nullptr, 0};
+    if (ep_in) ep = *ep_in;
+    if (ep.scale && !ep.shift) return INSMOS_ERR_INVALID_ARG;
+    if (n_out == 0) return INSMOS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (algo == 0) algo = (Cin >= 8 && Cout <= 128) ? 2 : 1;
+    if (algo == 2) {
+        const int nt8 = (Cout + 7) / 8;
+        if (nt8 <= 1) return launch_mma<1, 1>(in, weight, seg, entries, out, n_out, Cin, Cout, K, TM, ep, st);
+        if (nt8 <= 2) return launch_mma<2, 1>(in, weight, seg, entries, out, n_out, Cin, Cout, K, TM, ep, st);
+        if (nt8 <= 4) return launch_mma<2, 2>(in, weight, seg, entries, out, n_out, Cin, Cout, K, TM, ep, st);
+        if (nt8 <= 8) return launch_mma<2, 4>(in, weight, seg, entries, out, n_out, Cin, Cout, K, TM, ep, st);
+        if (nt8 <= 16) return launch_mma<4, 4>(in, weight, seg, entries, out, n_out, Cin, Cout, K, TM, ep, st);
+        return INSMOS_ERR_UNSUPPORTED;
+    }
+    if (algo != 1) return INSMOS_ERR_INVALID_ARG;
+    const size_t smem = sizeof(float) * (size_t)TM * Cout + sizeof(int) * (size_t)(K + 1);
+    if (smem > 220 * 1024) return INSMOS_ERR_UNSUPPORTED;
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_spconv_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    k_spconv_simt<<<(unsigned)ceil_div64(n_out, TM), SIMT_THREADS, smem, st>>>(in, weight, seg, entries, out, n_out,
+                                                                               Cin, Cout, K, TM, ep);
+    INSMOS_CHECK_LAUNCH("k_spconv_simt");
+    return INSMOS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_linear(const float* __restrict__ in, const float* __restrict__ W, float* __restrict__ out,
+                         int64_t n, int Cin, int Cout, insmos_epilogue_t ep) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * Cout) return;
+    const int64_t row = idx / Cout; const int co = (int)(idx - row * Cout);
+    const float* x = in + row * Cin;
+    float a = 0.0f;
+    for (int ci = 0; ci < Cin; ++ci) a = __fmaf_rn(__ldg(x + ci), __ldg(W + ci * Cout + co), a);
+    out[idx] = apply_epilogue(a, co, row, Cout, ep);
+}
+extern "C" int insmos_linear_fwd(const float* in, int64_t n, int32_t Cin, const float* weight, int32_t Cout,
+                                 float* out, const insmos_epilogue_t* ep_in, void* stream) {
+    if (!in || !weight || !out || Cin <= 0 || Cout <= 0 || n < 0) return INSMOS_ERR_INVALID_ARG;
+    insmos_epilogue_t ep = {nullptr, nullptr, nullptr, nullptr, 0};
+    if (ep_in) ep = *ep_in;
+    if (ep.scale && !ep.shift) return INSMOS_ERR_INVALID_ARG;
+    if (n == 0) return INSMOS_OK;
+    k_linear<<<(unsigned)ceil_div64(n * Cout, 256), 256, 0, (cudaStream_t)stream>>>(in, weight, out, n, Cin, Cout, ep);
+    INSMOS_CHECK_LAUNCH("k_linear");
+    return INSMOS_OK;
+}
+
+__global__ void k_affine_act(const float* __restrict__ x, float* __restrict__ out, int64_t n, int C, insmos_epilogue_t ep) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * C) return;
+    const int64_t row = idx / C; const int c = (int)(idx - row * C);
+    out[idx] = apply_epilogue(x[idx], c, row, C, ep);
+}
+extern "C" int insmos_affine_act(const float* x, int64_t n, int32_t C, float* out,
+                                 const insmos_epilogue_t* ep_in, void* stream) {
+    if (!x || !out || C <= 0 || n < 0 || !ep_in) return INSMOS_ERR_INVALID_ARG;
+    if (ep_in->scale && !ep_in->shift) return INSMOS_ERR_INVALID_ARG;
+    if (n == 0) return INSMOS_OK;
+    k_affine_act<<<(unsigned)ceil_div64(n * C, 256), 256, 0, (cudaStream_t)stream>>>(x, out, n, C, *ep_in);
+    INSMOS_CHECK_LAUNCH("k_affine_act");
+    return INSMOS_OK;
+}
+
+__global__ void k_concat2(const float* __restrict__ a, int C1, const float* __restrict__ b, int C2, int64_t n,
+                          float* __restrict__ out) {
+    const int C = C1 + C2;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * C) return;
+    const int64_t row = idx / C; const int c = (int)(idx - row * C);
+    out[idx] = (c < C1) ? a[row * C1 + c] : b[row * C2 + (c - C1)];
+}
+extern "C" int insmos_concat2(const float* a, int32_t C1, const float* b, int32_t C2, int64_t n,
+                              float* out, void* stream) {
+    if (!a || !b || !out || C1 <= 0 || C2 <= 0 || n < 0) return INSMOS_ERR_INVALID_ARG;
+    if (n == 0) return INSMOS_OK;
+    k_concat2<<<(unsigned)ceil_div64(n * (C1 + C2), 256), 256, 0, (cudaStream_t)stream>>>(a, C1, b, C2, n, out);
+    INSMOS_CHECK_LAUNCH("k_concat2");
+    return INSMOS_OK;
+}
+
+__global__ void k_pairsum_add(const float* __restrict__ a, const float* __restrict__ b, int64_t total, float* __restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const float2 v = reinterpret_cast<const float2*>(b)[idx];
+    const float s = __fadd_rn(v.x, v.y);
+    out[idx] = a ? __fadd_rn(a[idx], s) : s;
+}
+extern "C" int insmos_pairsum_add(const float* a, const float* b, int64_t n, int32_t C, float* out, void* stream) {
+    if (!b || !out || C <= 0 || n < 0) return INSMOS_ERR_INVALID_ARG;
+    if (n == 0) return INSMOS_OK;
+    k_pairsum_add<<<(unsigned)ceil_div64(n * C, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n * C, out);
+    INSMOS_CHECK_LAUNCH("k_pairsum_add");
+    return INSMOS_OK;
+}
+
+__global__ void k_gather_rows(const float* __restrict__ src, int C, const int32_t* __restrict__ idx, int64_t n,
+                              float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * C) return;
+    const int64_t row = i / C; const int c = (int)(i - row * C);
+    const int32_t s = idx[row];
+    out[i] = (s >= 0) ? src[(int64_t)s * C + c] : 0.0f;
+}
+extern "C" int insmos_gather_rows(const float* src, int32_t C, const int32_t* idx, int64_t n, float* out, void* stream) {
+    if (!src || !idx || !out || C <= 0 || n < 0) return INSMOS_ERR_INVALID_ARG;
+    if (n == 0) return INSMOS_OK;
+    k_gather_rows<<<(unsigned)ceil_div64(n * C, 256), 256, 0, (cudaStream_t)stream>>>(src, C, idx, n, out);
+    INSMOS_CHECK_LAUNCH("k_gather_rows");
+    return INSMOS_OK;
+}
+
+__global__ void k_seg_accum(const float* __restrict__ feat, int C, const int32_t* __restrict__ inverse, int64_t n,
+                            float* out, int32_t* cnt) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * C) return;
+    const int64_t row = i / C; const int c = (int)(i - row * C);
+    const int32_t r = inverse[row];
+    if (r < 0) return;
+    atomicAdd(out + (int64_t)r * C + c, feat[i]);
+    if (c == 0) atomicAdd(cnt + r, 1);
+}
+__global__ void k_seg_div(float* out, const int32_t* __restrict__ cnt, int64_t n_rows, int C) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * C) return;
+    const int32_t k = cnt[i / C];
+    out[i] = __fdiv_rn(out[i], (float)(k < 1 ? 1 : k));
+}
+extern "C" int insmos_segment_mean(const float* feat, int32_t C, const int32_t* inverse, int64_t n,
+                                   float* out, int32_t* cnt, int64_t n_rows, void* stream) {
+    if (!feat || !inverse || !out || !cnt || C <= 0 || n < 0 || n_rows < 0) return INSMOS_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_rows == 0) return INSMOS_OK;
+    INSMOS_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * n_rows * C, st));
+    INSMOS_CHECK_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * n_rows, st));
+    if (n > 0) {
+        k_seg_accum<<<(unsigned)ceil_div64(n * C, 256), 256, 0, st>>>(feat, C, inverse, n, out, cnt);
+        INSMOS_CHECK_LAUNCH("k_seg_accum");
+    }
+    k_seg_div<<<(unsigned)ceil_div64(n_rows * C, 256), 256, 0, st>>>(out, cnt, n_rows, C);
+    INSMOS_CHECK_LAUNCH("k_seg_div");
+    return INSMOS_OK;
+}
+
+__global__ void k_build_current(const float* __restrict__ points, int stride, const int32_t* __restrict__ cur_index,
+                                int64_t n_cur, const int32_t* __restrict__ inverse, const float* __restrict__ vox_feat,
+                                int Cfeat, int Cm, float* __restrict__ out) {
+    const int CO = 4 + Cm;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cur * CO) return;
+    const int64_t j = i / CO; const int c = (int)(i - j * CO);
+    const int32_t p = cur_index[j];
+    float v;
+    if (c < 4) v = points[(int64_t)p * stride + c];
+    else { const int32_t r = inverse[p]; v = (r >= 0) ? vox_feat[(int64_t)r * Cfeat + (c - 4)] : 0.0f; }
+    out[i] = v;
+}
+extern "C" int insmos_build_current_points(const float* points, int32_t point_stride, const int32_t* cur_index,
+                                           int64_t n_cur, const int32_t* inverse, const float* vox_feat, int32_t Cfeat,
+                                           int32_t Cm, float* out, void* stream) {
+    if (!points || !cur_index || !inverse || !vox_feat || !out || Cm <= 0 || Cm > Cfeat || point_stride < 4 || n_cur < 0)
+        return INSMOS_ERR_INVALID_ARG;
+    if (n_cur == 0) return INSMOS_OK;
+    k_build_current<<<(unsigned)ceil_div64(n_cur * (4 + Cm), 256), 256, 0, (cudaStream_t)stream>>>(
+        points, point_stride, cur_index, n_cur, inverse, vox_feat, Cfeat, Cm, out);
+    INSMOS_CHECK_LAUNCH("k_build_current");
+    return INSMOS_OK;
+}
+
+__global__ void k_dense_scatter(const float* __restrict__ feat, const int32_t* __restrict__ coords, int64_t n, int C,
+                                int D, int H, int W, float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * C) return;
+    const int64_t row = i / C; const int c = (int)(i - row * C);
+    const int32_t* p = coords + row * 4;
+    const int z = p[1], y = p[2], x = p[3];
+    if ((unsigned)z >= (unsigned)D || (unsigned)y >= (unsigned)H || (unsigned)x >= (unsigned)W) return;
+    out[(((int64_t)c * D + z) * H + y) * W + x] = feat[i];
+}
+extern "C" int insmos_dense_scatter(const float* feat, const int32_t* coords, int64_t n, int32_t C,
+                                    int32_t D, int32_t H, int32_t W, float* out, void* stream) {
+    if (!feat || !coords || !out || C <= 0 || D <= 0 || H <= 0 || W <= 0 || n < 0) return INSMOS_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    INSMOS_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)C * D * H * W, st));
+    if (n == 0) return INSMOS_OK;
+    k_dense_scatter<<<(unsigned)ceil_div64(n * C, 256), 256, 0, st>>>(feat, coords, n, C, D, H, W, out);
+    INSMOS_CHECK_LAUNCH("k_dense_scatter");
+    return INSMOS_OK;
+}

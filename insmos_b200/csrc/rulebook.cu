@@ -1,0 +1,168 @@
+// Rule-book (kernel map / indice pair) construction.  SURVEY.md section 8 rows a4, a8, a12.
+//
+// Layout is output-stationary and tiled for the convolution kernels in conv.cu:
+//   * output rows are cut into tiles of TM consecutive rows,
+//   * tile t owns the fixed slab entries[t*TM*K, (t+1)*TM*K) -- no global scan, no atomics, the
+//     layout is a pure function of the inputs (deterministic); only the occupied prefix of a slab
+//     is ever touched, so DRAM traffic is 4 bytes per pair (the COO form is 8),
+//   * inside a tile the pairs are bucketed by kernel offset k (seg[t][k] .. seg[t][k+1]) and, inside
+//     a bucket, ordered by output row.  Within one bucket every output row appears at most once,
+//     which is what lets the convolution accumulate a bucket into its shared-memory tile without
+//     atomics.
+//   * entry = (out_row_in_tile << 25) | in_row.
+// One block builds one tile: TM*K hash probes (16-byte slot loads, L2 resident table) staged in
+// shared memory, then one warp per offset compacts its bucket with ballots.
+#include "common.cuh"
+
+#define RB_THREADS 256
+
+extern "C" int64_t insmos_rulebook_entries_capacity(int64_t n_out, int32_t K, int32_t TM) {
+    if (n_out <= 0 || K <= 0 || TM <= 0) return 0;
+    return ceil_div64(n_out, TM) * (int64_t)TM * K;
+}
+
+__global__ void __launch_bounds__(RB_THREADS)
+k_rulebook_tiles(const int32_t* __restrict__ out_coords, int64_t n_out,
+                 const insmos_slot_t* __restrict__ table, uint64_t mask,
+                 insmos_mapspec_t spec, int TM,
+                 uint16_t* __restrict__ seg, uint32_t* __restrict__ entries,
+                 unsigned long long* pair_count) {
+    extern __shared__ int smem[];
+    const int K = spec.K, ncol = spec.ncol, ndim = spec.ndim;
+    int* nbr = smem;                       // [TM*K] in-row or -1
+    int* tc = nbr + TM * K;                // [TM*5] coordinates of the tile's rows
+    int* kd = tc + TM * 5;                 // [K*4]  per-offset per-dim term
+    int* hist = kd + K * 4;                // [K+1]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = RB_THREADS / 32;
+    const int64_t tile = blockIdx.x;
+    const int64_t row0 = tile * TM;
+
+    for (int i = tid; i < TM * ncol; i += RB_THREADS) {
+        const int64_t g = row0 * ncol + i;
+        tc[(i / ncol) * 5 + (i % ncol)] = (g < n_out * ncol) ? out_coords[g] : 0;
+    }
+    for (int k = tid; k < K; k += RB_THREADS) {
+        int rem = k;
+        int dig[4] = {0, 0, 0, 0};
+        if (spec.first_fastest) { for (int d = 0; d < ndim; ++d) { dig[d] = rem % spec.ksize[d]; rem /= spec.ksize[d]; } }
+        else { for (int d = ndim - 1; d >= 0; --d) { dig[d] = rem % spec.ksize[d]; rem /= spec.ksize[d]; } }
+        for (int d = 0; d < 4; ++d)
+            kd[k * 4 + d] = (d < ndim) ? (spec.mode == 0 ? spec.b[d] + dig[d] * spec.e[d] : dig[d]) : 0;
+    }
+    __syncthreads();
+
+    // ---- phase A: probe
+    const int total = TM * K;
+    for (int idx = tid; idx < total; idx += RB_THREADS) {
+        const int r = idx / K, k = idx - r * K;
+        int res = -1;
+        if (row0 + r < n_out) {
+            const int* c = tc + r * 5;
+            int ci[4] = {0, 0, 0, 0};
+            bool ok = true;
+            if (spec.mode == 0) {
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    if (d < ndim) {
+                        int v = c[1 + d] * spec.a[d] + kd[k * 4 + d];
+                        const int q = spec.q[d];
+                        if (q > 1) { if (v % q) ok = false; v /= q; }
+                        ci[d] = v;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    if (d < ndim) {
+                        const int base = floor_div(c[1 + d], spec.up_q[d]) * spec.up_q[d];
+                        if ((c[1 + d] - base) / spec.up_ts[d] != kd[k * 4 + d]) ok = false;
+                        ci[d] = base;
+                    }
+                }
+            }
+            if (ok && coord_in_range(c[0], ci[0], ci[1], ci[2], ci[3]))
+                res = table_find_row(table, mask, pack_key(c[0], ci[0], ci[1], ci[2], ci[3]));
+        }
+        nbr[idx] = res;
+    }
+    __syncthreads();
+
+    // ---- phase B: bucket sizes (one warp per offset)
+    for (int k = warp; k < K; k += nwarps) {
+        int cnt = 0;
+        for (int r0 = 0; r0 < TM; r0 += 32) {
+            const int r = r0 + lane;
+            const bool hit = (r < TM) && nbr[r * K + k] >= 0;
+            cnt += __popc(__ballot_sync(0xffffffffu, hit));
+        }
+        if (lane == 0) hist[k] = cnt;
+    }
+    __syncthreads();
+    if (warp == 0) {                                  // exclusive scan of hist[0..K) -> hist, hist[K] = total
+        int carry = 0;
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            const int k = k0 + lane;
+            const int v = (k < K) ? hist[k] : 0;
+            int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            if (k < K) hist[k] = carry + inc - v;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) {
+            hist[K] = carry;
+            if (pair_count && carry) atomicAdd(pair_count, (unsigned long long)carry);
+        }
+    }
+    __syncthreads();
+    uint16_t* tseg = seg + tile * (K + 1);
+    for (int k = tid; k <= K; k += RB_THREADS) tseg[k] = (uint16_t)hist[k];
+
+    // ---- phase C: compact each bucket in output-row order
+    uint32_t* tent = entries + tile * (int64_t)TM * K;
+    for (int k = warp; k < K; k += nwarps) {
+        int pos = hist[k];
+        for (int r0 = 0; r0 < TM; r0 += 32) {
+            const int r = r0 + lane;
+            const int v = (r < TM) ? nbr[r * K + k] : -1;
+            const unsigned bal = __ballot_sync(0xffffffffu, v >= 0);
+            if (v >= 0) tent[pos + __popc(bal & ((1u << lane) - 1u))] = ((uint32_t)r << INSMOS_ROW_BITS) | (uint32_t)v;
+            pos += __popc(bal);
+        }
+    }
+}
+
+extern "C" int insmos_rulebook_build(const int32_t* out_coords, int64_t n_out,
+                                     const insmos_slot_t* in_table, int64_t in_cap,
+                                     const insmos_mapspec_t* spec, int32_t TM,
+                                     uint16_t* seg, uint32_t* entries, unsigned long long* pair_count,
+                                     int32_t* counters, void* stream) {
+    (void)counters;
+    if (!out_coords || !in_table || !spec || !seg || !entries || n_out < 0) return INSMOS_ERR_INVALID_ARG;
+    if (in_cap <= 0 || (in_cap & (in_cap - 1))) return INSMOS_ERR_INVALID_ARG;
+    if (TM != 16 && TM != 32 && TM != 64 && TM != 128) return INSMOS_ERR_INVALID_ARG;
+    if (spec->K <= 0 || (int64_t)TM * spec->K >= 65536 || spec->ndim < 1 || spec->ndim > 4 ||
+        (spec->ncol != 4 && spec->ncol != 5) || spec->ndim > spec->ncol - 1)
+        return INSMOS_ERR_INVALID_ARG;
+    int kprod = 1;
+    for (int d = 0; d < spec->ndim; ++d) {
+        if (spec->ksize[d] < 1) return INSMOS_ERR_INVALID_ARG;
+        if (spec->mode == 0 && spec->q[d] < 1) return INSMOS_ERR_INVALID_ARG;
+        if (spec->mode == 1 && (spec->up_q[d] < 1 || spec->up_ts[d] < 1)) return INSMOS_ERR_INVALID_ARG;
+        kprod *= spec->ksize[d];
+    }
+    if (kprod != spec->K) return INSMOS_ERR_INVALID_ARG;
+    if (n_out == 0) return INSMOS_OK;
+    const size_t smem = sizeof(int) * ((size_t)TM * spec->K + (size_t)TM * 5 + (size_t)spec->K * 4 + spec->K + 1);
+    if (smem > 220 * 1024) return INSMOS_ERR_UNSUPPORTED;
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_rulebook_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int64_t n_tiles = ceil_div64(n_out, TM);
+    k_rulebook_tiles<<<(unsigned)n_tiles, RB_THREADS, smem, (cudaStream_t)stream>>>(
+        out_coords, n_out, in_table, (uint64_t)(in_cap - 1), *spec, TM, seg, entries, pair_count);
+    INSMOS_CHECK_LAUNCH("k_rulebook_tiles");
+    return INSMOS_OK;
+}
