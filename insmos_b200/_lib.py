@@ -1,0 +1,100 @@
+"""ctypes binding of libinsmos_b200.so (C ABI declared in include/insmos_b200.h).
+
+There is no CPU fallback: if the shared library is missing the import of any product op fails
+with a RuntimeError that says how to build it.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libinsmos_b200.so")
+
+OK = 0
+ERRORS = {-1: "INVALID_ARG", -2: "CUDA", -3: "UNSUPPORTED"}
+DEVERR_COORD_RANGE = 1
+CNT_ROWS, CNT_AUX, CNT_ERR, CNT_TOTAL, NUM_COUNTERS = 0, 1, 2, 3, 4
+ROW_BITS = 25
+
+
+class MapSpec(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("ncol", C.c_int32), ("ndim", C.c_int32), ("first_fastest", C.c_int32),
+                ("K", C.c_int32), ("ksize", C.c_int32 * 4), ("a", C.c_int32 * 4), ("b", C.c_int32 * 4),
+                ("e", C.c_int32 * 4), ("q", C.c_int32 * 4), ("up_q", C.c_int32 * 4), ("up_ts", C.c_int32 * 4)]
+
+
+class Epilogue(C.Structure):
+    _fields_ = [("scale", C.c_void_p), ("shift", C.c_void_p), ("bias", C.c_void_p), ("residual", C.c_void_p),
+                ("relu", C.c_int32)]
+
+
+_P = C.c_void_p
+_I64 = C.c_int64
+_I32 = C.c_int32
+_F = C.c_float
+
+# name -> (restype, argtypes); kept in one table so tests can check every symbol of the header
+PROTOTYPES = {
+    "insmos_version": (C.c_char_p, []),
+    "insmos_last_error": (C.c_char_p, []),
+    "insmos_hash_capacity": (_I64, [_I64]),
+    "insmos_scan_scratch_bytes": (_I64, [_I64]),
+    "insmos_table_clear": (C.c_int, [_P, _I64, _P]),
+    "insmos_voxelize4d": (C.c_int, [_P, _I64, _I32, C.POINTER(_F), _P, _I64, _P, _P, _P, _P, _P, _P, _P]),
+    "insmos_unique_coords": (C.c_int, [_P, _I64, _I32, C.POINTER(_I32), _P, _I64, _P, _P, _P, _P, _P, _P]),
+    "insmos_spconv_out_scratch_bytes": (_I64, [_I64, _I32]),
+    "insmos_spconv_out_coords": (C.c_int, [_P, _I64, C.POINTER(_I32), C.POINTER(_I32), C.POINTER(_I32),
+                                           C.POINTER(_I32), _P, _I64, _P, _P, _P, _P]),
+    "insmos_voxelize3d": (C.c_int, [_P, _I64, _I32, C.POINTER(_F), C.POINTER(_F), C.POINTER(_I32), _I32, _I32,
+                                    _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "insmos_rulebook_entries_capacity": (_I64, [_I64, _I32, _I32]),
+    "insmos_rulebook_build": (C.c_int, [_P, _I64, _P, _I64, C.POINTER(MapSpec), _I32, _P, _P, _P, _P, _P]),
+    "insmos_sparse_conv_fwd": (C.c_int, [_P, _I64, _I32, _P, _I32, _I32, _P, _P, _I32, _P, _I64,
+                                         C.POINTER(Epilogue), _I32, _P]),
+    "insmos_linear_fwd": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, C.POINTER(Epilogue), _P]),
+    "insmos_affine_act": (C.c_int, [_P, _I64, _I32, _P, C.POINTER(Epilogue), _P]),
+    "insmos_concat2": (C.c_int, [_P, _I32, _P, _I32, _I64, _P, _P]),
+    "insmos_pairsum_add": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
+    "insmos_gather_rows": (C.c_int, [_P, _I32, _P, _I64, _P, _P]),
+    "insmos_segment_mean": (C.c_int, [_P, _I32, _P, _I64, _P, _P, _I64, _P]),
+    "insmos_build_current_points": (C.c_int, [_P, _I32, _P, _I64, _P, _P, _I32, _I32, _P, _P]),
+    "insmos_dense_scatter": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P]),
+    "insmos_center_decode": (C.c_int, [_P, _P, _I32, _I32, _I32, _F, _F, _F, _F, _F, _P, _P, _P, _P]),
+    "insmos_nms_rotated": (C.c_int, [_P, _I32, _F, _I32, _P, _P, _P, _P]),
+    "insmos_boxes_to_voxel_units": (C.c_int, [_P, _P, _I32, C.POINTER(_F), C.POINTER(_F), _F, _P, _P]),
+    "insmos_box_membership": (C.c_int, [_P, _I64, _P, _I32, _F, _P, _I32, _P, _P]),
+}
+
+_lib = None
+LAUNCHES = 0          # number of C-ABI calls that launch kernels (bench.py reports it)
+
+
+def load():
+    """Load the shared library (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "insmos_b200: %s is missing. Build it with `python -m insmos_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)          # AttributeError if the library does not export the symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != OK:
+        detail = ""
+        if rc == -2:
+            detail = ": " + load().insmos_last_error().decode()
+        raise RuntimeError("insmos_b200: %s failed with %s%s" % (what, ERRORS.get(rc, rc), detail))
+
+
+def call(name, *args):
+    global LAUNCHES
+    LAUNCHES += 1
+    check(getattr(load(), name)(*args), name)

@@ -1,0 +1,422 @@
+"""Tensor-level wrappers over the C ABI (include/insmos_b200.h).
+
+PyTorch is used for device memory (caching allocator), the current stream and the small host
+read-backs of data-dependent sizes -- plumbing.  All arithmetic happens in libinsmos_b200.so.
+Every function requires CUDA tensors; there is no CPU path.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import MapSpec, Epilogue, call
+
+I32 = torch.int32
+F32 = torch.float32
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _req(t, dtype, name):
+    if not t.is_cuda:
+        raise RuntimeError("insmos_b200.%s: CUDA tensor required (no CPU fallback)" % name)
+    if t.dtype != dtype:
+        raise TypeError("insmos_b200.%s: expected %s, got %s" % (name, dtype, t.dtype))
+    return t.contiguous()
+
+
+def _arr(ctype, vals):
+    return (ctype * len(vals))(*vals)
+
+
+def _read_counters(counters, what):
+    c = counters.cpu().tolist()            # one small D2H read; the only sync of a coordinate op
+    if c[_lib.CNT_ERR] & _lib.DEVERR_COORD_RANGE:
+        raise RuntimeError("insmos_b200.%s: coordinate outside the packable range "
+                           "(|x|,|y|,|z| < 32768 voxels, |t| < 128, batch < 255)" % what)
+    return c
+
+
+def _scan_scratch(n, device):
+    return torch.empty(_lib.load().insmos_scan_scratch_bytes(int(n)), dtype=torch.uint8, device=device)
+
+
+class CoordSet:
+    """Unique integer coordinates [n, ncol] (batch first) plus the hash table that maps a
+    coordinate to its row.  Equivalent of an ME coordinate-map key / spconv indices."""
+
+    def __init__(self, coords, n, table, cap, tensor_stride=None):
+        self.coords, self.n, self.table, self.cap = coords, int(n), table, int(cap)
+        self.tensor_stride = tensor_stride
+        self.ncol = coords.shape[1]
+
+
+def _new_table(n, device):
+    lib = _lib.load()
+    cap = lib.insmos_hash_capacity(int(max(n, 1)))
+    table = torch.empty((cap, 2), dtype=torch.int64, device=device)
+    call("insmos_table_clear", _p(table), cap, _stream())
+    return table, cap
+
+
+def voxelize4d(points, quant):
+    """a1+a2: points [N,>=5] f32 (x,y,z,intensity,t) -> (CoordSet (0,x,y,z,t), inverse [N] i32, cur_index [Nc] i32)."""
+    points = _req(points, F32, "voxelize4d")
+    n, stride = points.shape
+    dev = points.device
+    table, cap = _new_table(n, dev)
+    slot = torch.empty(max(n, 1), dtype=I32, device=dev)
+    coords = torch.empty((max(n, 1), 5), dtype=I32, device=dev)
+    inverse = torch.empty(max(n, 1), dtype=I32, device=dev)
+    cur = torch.empty(max(n, 1), dtype=I32, device=dev)
+    counters = torch.zeros(_lib.NUM_COUNTERS, dtype=I32, device=dev)
+    call("insmos_voxelize4d", _p(points), n, stride, _arr(C.c_float, [float(q) for q in quant]), _p(table), cap,
+         _p(slot), _p(coords), _p(inverse), _p(cur), _p(counters), _p(_scan_scratch(n, dev)), _stream())
+    c = _read_counters(counters, "voxelize4d")
+    nv, nc = c[_lib.CNT_ROWS], c[_lib.CNT_AUX]
+    return CoordSet(coords[:nv], nv, table, cap), inverse[:n], cur[:nc]
+
+
+def unique_coords(coords, q=None):
+    """unique int32 rows [N,ncol] in first-occurrence order (optionally floored to multiples of q)."""
+    coords = _req(coords, I32, "unique_coords")
+    n, ncol = coords.shape
+    dev = coords.device
+    table, cap = _new_table(n, dev)
+    slot = torch.empty(max(n, 1), dtype=I32, device=dev)
+    out = torch.empty((max(n, 1), ncol), dtype=I32, device=dev)
+    inverse = torch.empty(max(n, 1), dtype=I32, device=dev)
+    counters = torch.zeros(_lib.NUM_COUNTERS, dtype=I32, device=dev)
+    qa = None if q is None else _arr(C.c_int32, [int(v) for v in q])
+    call("insmos_unique_coords", _p(coords), n, ncol, qa, _p(table), cap, _p(slot), _p(out), _p(inverse),
+         _p(counters), _p(_scan_scratch(n, dev)), _stream())
+    c = _read_counters(counters, "unique_coords")
+    nv = c[_lib.CNT_ROWS]
+    return CoordSet(out[:nv], nv, table, cap), inverse[:n]
+
+
+def spconv_out_coords(in_set, ksize, stride, pad, out_shape):
+    """output coordinates of a strided spconv SparseConv3d (oracle order)."""
+    lib = _lib.load()
+    n = in_set.n
+    K = int(ksize[0] * ksize[1] * ksize[2])
+    dev = in_set.coords.device
+    table, cap = _new_table(n * K, dev)
+    out = torch.empty((max(n * K, 1), 4), dtype=I32, device=dev)
+    counters = torch.zeros(_lib.NUM_COUNTERS, dtype=I32, device=dev)
+    scratch = torch.empty(lib.insmos_spconv_out_scratch_bytes(n, K), dtype=torch.uint8, device=dev)
+    call("insmos_spconv_out_coords", _p(in_set.coords), n, _arr(C.c_int32, list(ksize)), _arr(C.c_int32, list(stride)),
+         _arr(C.c_int32, list(pad)), _arr(C.c_int32, list(out_shape)), _p(table), cap, _p(out), _p(counters),
+         _p(scratch), _stream())
+    c = _read_counters(counters, "spconv_out_coords")
+    nv = c[_lib.CNT_ROWS]
+    return CoordSet(out[:nv].clone(), nv, table, cap)
+
+
+def voxelize3d(points, pc_range, vsize, grid, max_voxels, max_points, want_voxels=False):
+    """a6+a7: capped voxelisation with ids and fused mean.  Returns dict with CoordSet 'set' (0,z,y,x),
+    'mean' [M,C], 'num_points' [M] i32, 'pc_voxel_id' [N] i32, optional 'voxels' [M,max_points,C]."""
+    points = _req(points, F32, "voxelize3d")
+    n, Cc = points.shape
+    dev = points.device
+    table, cap = _new_table(n, dev)
+    slot = torch.empty(max(n, 1), dtype=I32, device=dev)
+    mv = int(max_voxels)
+    rows_cap = max(min(n, mv), 1)
+    coords = torch.empty((rows_cap, 4), dtype=I32, device=dev)
+    num = torch.empty(rows_cap, dtype=I32, device=dev)
+    voxels = torch.empty((rows_cap, max_points, Cc), dtype=F32, device=dev) if want_voxels else None
+    mean = torch.empty((rows_cap, Cc), dtype=F32, device=dev)
+    ids = torch.empty(max(n, 1), dtype=I32, device=dev)
+    work = torch.empty(mv * (1 + max_points), dtype=I32, device=dev)
+    counters = torch.zeros(_lib.NUM_COUNTERS, dtype=I32, device=dev)
+    call("insmos_voxelize3d", _p(points), n, Cc, _arr(C.c_float, [float(v) for v in pc_range]),
+         _arr(C.c_float, [float(v) for v in vsize]), _arr(C.c_int32, [int(v) for v in grid]), mv, int(max_points),
+         _p(table), cap, _p(slot), _p(coords), _p(num), _p(voxels), _p(mean), _p(ids), _p(work), _p(counters),
+         _p(_scan_scratch(n, dev)), _stream())
+    c = _read_counters(counters, "voxelize3d")
+    m = c[_lib.CNT_ROWS]
+    out = {"set": CoordSet(coords[:m], m, table, cap), "mean": mean[:m], "num_points": num[:m],
+           "pc_voxel_id": ids[:n], "n_distinct": c[_lib.CNT_TOTAL]}
+    if want_voxels:
+        out["voxels"] = voxels[:m]
+    return out
+
+
+# ---- rule books ---------------------------------------------------------------------------------
+def _spec(mode, ncol, ndim, first_fastest, ksize, a=None, b=None, e=None, q=None, up_q=None, up_ts=None):
+    s = MapSpec()
+    s.mode, s.ncol, s.ndim, s.first_fastest = mode, ncol, ndim, first_fastest
+    K = 1
+    for d in range(4):
+        s.ksize[d] = int(ksize[d]) if d < ndim else 1
+        K *= s.ksize[d]
+        s.a[d] = int(a[d]) if a is not None and d < ndim else 1
+        s.b[d] = int(b[d]) if b is not None and d < ndim else 0
+        s.e[d] = int(e[d]) if e is not None and d < ndim else 1
+        s.q[d] = int(q[d]) if q is not None and d < ndim else 1
+        s.up_q[d] = int(up_q[d]) if up_q is not None and d < ndim else 1
+        s.up_ts[d] = int(up_ts[d]) if up_ts is not None and d < ndim else 1
+    s.K = K
+    return s
+
+
+def spec_me_cube(ksize, in_stride):
+    """MinkowskiConvolution hyper-cube kernel (any stride): in = out + offset*in_stride; odd sizes are
+    centred, even sizes start at 0."""
+    D = len(ksize)
+    b = [-((k - 1) // 2) * t if k % 2 == 1 else 0 for k, t in zip(ksize, in_stride)]
+    return _spec(0, D + 1, D, 1, ksize, a=[1] * D, b=b, e=list(in_stride), q=[1] * D)
+
+
+def spec_me_up(ksize, stride, out_stride):
+    """MinkowskiConvolutionTranspose with kernel == stride (2,2,2,1): out = fine rows, in = coarse parent."""
+    D = len(ksize)
+    up_q = [s * t for s, t in zip(stride, out_stride)]
+    return _spec(1, D + 1, D, 1, ksize, up_q=up_q, up_ts=list(out_stride))
+
+
+def spec_sp_subm(ksize):
+    return _spec(0, 4, 3, 0, ksize, a=[1, 1, 1], b=[-(k // 2) for k in ksize], e=[1, 1, 1], q=[1, 1, 1])
+
+
+def spec_sp_conv(ksize, stride, pad):
+    return _spec(0, 4, 3, 0, ksize, a=list(stride), b=[-p for p in pad], e=[1, 1, 1], q=[1, 1, 1])
+
+
+def spec_sp_inverse(ksize, stride, pad):
+    return _spec(0, 4, 3, 0, ksize, a=[1, 1, 1], b=list(pad), e=[-1, -1, -1], q=list(stride))
+
+
+class Rulebook:
+    def __init__(self, seg, entries, TM, K, n_out, n_in, pair_count):
+        self.seg, self.entries, self.TM, self.K = seg, entries, TM, K
+        self.n_out, self.n_in, self.pair_count = n_out, n_in, pair_count
+        self._pairs = None
+
+    @property
+    def num_pairs(self):
+        if self._pairs is None:
+            self._pairs = int(self.pair_count.item())
+        return self._pairs
+
+    def to_coo(self):
+        """decode to sorted (k, in_row, out_row) int64 triples -- for tests / statistics only."""
+        K, TM = self.K, self.TM
+        n_tiles = (self.n_out + TM - 1) // TM
+        seg = (self.seg.view(torch.int16).to(torch.int32) & 0xFFFF).view(n_tiles, K + 1).cpu()
+        ent = self.entries.view(n_tiles, TM * K).cpu()
+        ks, ins, outs = [], [], []
+        for t in range(n_tiles):
+            tot = int(seg[t, K])
+            if tot == 0:
+                continue
+            e = ent[t, :tot].to(torch.int64) & 0xFFFFFFFF
+            counts = (seg[t, 1:] - seg[t, :-1]).to(torch.int64)
+            ks.append(torch.repeat_interleave(torch.arange(K, dtype=torch.int64), counts))
+            ins.append(e & ((1 << _lib.ROW_BITS) - 1))
+            outs.append((e >> _lib.ROW_BITS) + t * TM)
+        if not ks:
+            return torch.zeros((0, 3), dtype=torch.int64)
+        trip = torch.stack([torch.cat(ks), torch.cat(ins), torch.cat(outs)], dim=1)
+        key = (trip[:, 0] * (self.n_in + 1) + trip[:, 1]) * (self.n_out + 1) + trip[:, 2]
+        return trip[torch.argsort(key)]
+
+
+def choose_tile_rows(n_out, K):
+    tm = 128 if n_out >= 300_000 else 64 if n_out >= 100_000 else 32 if n_out >= 20_000 else 16
+    while tm > 16 and tm * K >= 65536:
+        tm //= 2
+    return tm
+
+
+def build_rulebook(out_set, in_set, spec, TM=None):
+    lib = _lib.load()
+    K = int(spec.K)
+    n_out = out_set.n
+    if TM is None:
+        TM = choose_tile_rows(n_out, K)
+    dev = out_set.coords.device
+    n_tiles = max((n_out + TM - 1) // TM, 1)
+    seg = torch.empty(n_tiles * (K + 1), dtype=torch.int16, device=dev)
+    entries = torch.empty(max(lib.insmos_rulebook_entries_capacity(max(n_out, 1), K, TM), 1), dtype=I32, device=dev)
+    pc = torch.zeros(1, dtype=torch.int64, device=dev)
+    if in_set.n > (1 << _lib.ROW_BITS):
+        raise RuntimeError("insmos_b200.build_rulebook: more than 2^25 input rows")
+    call("insmos_rulebook_build", _p(out_set.coords), n_out, _p(in_set.table), in_set.cap, C.byref(spec), TM,
+         _p(seg), _p(entries), _p(pc), None, _stream())
+    return Rulebook(seg, entries, TM, K, n_out, in_set.n, pc)
+
+
+# ---- feature ops --------------------------------------------------------------------------------
+def _epilogue(scale=None, shift=None, bias=None, residual=None, relu=False):
+    ep = Epilogue()
+    keep = []
+    for name, t in (("scale", scale), ("shift", shift), ("bias", bias), ("residual", residual)):
+        if t is not None:
+            t = _req(t, F32, "epilogue." + name)
+            keep.append(t)
+            setattr(ep, name, t.data_ptr())
+        else:
+            setattr(ep, name, None)
+    ep.relu = 1 if relu else 0
+    return ep, keep
+
+
+def sparse_conv(feat, weight, rb, scale=None, shift=None, bias=None, residual=None, relu=False, algo=0):
+    """out[n_out,Cout] = sum over rule-book pairs of feat[in] @ weight[k] (+ fused epilogue).
+    weight [K,Cin,Cout] f32."""
+    feat = _req(feat, F32, "sparse_conv")
+    weight = _req(weight, F32, "sparse_conv")
+    K, Cin, Cout = weight.shape
+    if K != rb.K or feat.shape[1] != Cin or feat.shape[0] != rb.n_in:
+        raise ValueError("sparse_conv: shape mismatch (feat %s, weight %s, rule book K=%d n_in=%d)"
+                         % (tuple(feat.shape), tuple(weight.shape), rb.K, rb.n_in))
+    out = torch.empty((rb.n_out, Cout), dtype=F32, device=feat.device)
+    ep, keep = _epilogue(scale, shift, bias, residual, relu)
+    call("insmos_sparse_conv_fwd", _p(feat), rb.n_in, Cin, _p(weight), K, Cout, _p(rb.seg), _p(rb.entries), rb.TM,
+         _p(out), rb.n_out, C.byref(ep), int(algo), _stream())
+    return out
+
+
+def linear(feat, weight, scale=None, shift=None, bias=None, residual=None, relu=False):
+    """out = feat[n,Cin] @ weight[Cin,Cout] (+ fused epilogue)."""
+    feat = _req(feat, F32, "linear")
+    weight = _req(weight, F32, "linear")
+    Cin, Cout = weight.shape
+    n = feat.shape[0]
+    out = torch.empty((n, Cout), dtype=F32, device=feat.device)
+    ep, keep = _epilogue(scale, shift, bias, residual, relu)
+    call("insmos_linear_fwd", _p(feat), n, Cin, _p(weight), Cout, _p(out), C.byref(ep), _stream())
+    return out
+
+
+def affine_act(x, scale=None, shift=None, bias=None, residual=None, relu=False, out=None):
+    x = _req(x, F32, "affine_act")
+    n, Cc = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    ep, keep = _epilogue(scale, shift, bias, residual, relu)
+    call("insmos_affine_act", _p(x), n, Cc, _p(out), C.byref(ep), _stream())
+    return out
+
+
+def concat2(a, b):
+    a = _req(a, F32, "concat2")
+    b = _req(b, F32, "concat2")
+    n = a.shape[0]
+    out = torch.empty((n, a.shape[1] + b.shape[1]), dtype=F32, device=a.device)
+    call("insmos_concat2", _p(a), a.shape[1], _p(b), b.shape[1], n, _p(out), _stream())
+    return out
+
+
+def pairsum_add(a, b):
+    """a[n,C] + b[n,2C].view(n,C,2).sum(2); a may be None."""
+    b = _req(b, F32, "pairsum_add")
+    n, C2 = b.shape
+    out = torch.empty((n, C2 // 2), dtype=F32, device=b.device)
+    if a is not None:
+        a = _req(a, F32, "pairsum_add")
+    call("insmos_pairsum_add", _p(a), _p(b), n, C2 // 2, _p(out), _stream())
+    return out
+
+
+def gather_rows(src, idx):
+    src = _req(src, F32, "gather_rows")
+    idx = _req(idx, I32, "gather_rows")
+    n = idx.shape[0]
+    out = torch.empty((n, src.shape[1]), dtype=F32, device=src.device)
+    call("insmos_gather_rows", _p(src), src.shape[1], _p(idx), n, _p(out), _stream())
+    return out
+
+
+def segment_mean(feat, inverse, n_rows):
+    feat = _req(feat, F32, "segment_mean")
+    inverse = _req(inverse, I32, "segment_mean")
+    n, Cc = feat.shape
+    out = torch.empty((max(n_rows, 1), Cc), dtype=F32, device=feat.device)
+    cnt = torch.empty(max(n_rows, 1), dtype=I32, device=feat.device)
+    call("insmos_segment_mean", _p(feat), Cc, _p(inverse), n, _p(out), _p(cnt), n_rows, _stream())
+    return out[:n_rows]
+
+
+def build_current_points(points, cur_index, inverse, vox_feat, n_motion):
+    points = _req(points, F32, "build_current_points")
+    vox_feat = _req(vox_feat, F32, "build_current_points")
+    nc = cur_index.shape[0]
+    out = torch.empty((nc, 4 + n_motion), dtype=F32, device=points.device)
+    call("insmos_build_current_points", _p(points), points.shape[1], _p(cur_index), nc, _p(inverse), _p(vox_feat),
+         vox_feat.shape[1], n_motion, _p(out), _stream())
+    return out
+
+
+def dense_scatter(feat, coords, D, H, W):
+    feat = _req(feat, F32, "dense_scatter")
+    coords = _req(coords, I32, "dense_scatter")
+    n, Cc = feat.shape
+    out = torch.empty((Cc, D, H, W), dtype=F32, device=feat.device)
+    call("insmos_dense_scatter", _p(feat), _p(coords), n, Cc, D, H, W, _p(out), _stream())
+    return out
+
+
+# ---- detection head -----------------------------------------------------------------------------
+def center_decode(cls, box, out_size_factor, vx, vy, x_min, y_min):
+    """cls [ncls,H,W], box [8,H,W] -> boxes [HW,7], scores [HW], labels [HW] i32 (1-based)."""
+    cls = _req(cls, F32, "center_decode")
+    box = _req(box, F32, "center_decode")
+    ncls, H, W = cls.shape
+    dev = cls.device
+    boxes = torch.empty((H * W, 7), dtype=F32, device=dev)
+    scores = torch.empty(H * W, dtype=F32, device=dev)
+    labels = torch.empty(H * W, dtype=I32, device=dev)
+    call("insmos_center_decode", _p(cls), _p(box), ncls, H, W, float(out_size_factor), float(vx), float(vy),
+         float(x_min), float(y_min), _p(boxes), _p(scores), _p(labels), _stream())
+    return boxes, scores, labels
+
+
+def nms_rotated(boxes_sorted, thresh, max_keep):
+    """boxes [n,7] sorted by descending score -> keep indices (ascending, <= max_keep) as i32 tensor."""
+    boxes_sorted = _req(boxes_sorted, F32, "nms_rotated")
+    n = boxes_sorted.shape[0]
+    dev = boxes_sorted.device
+    cb = (n + 63) // 64
+    mask = torch.empty(max(n * cb, 1), dtype=torch.int64, device=dev)
+    keep = torch.empty(max(min(n, max_keep), 1), dtype=I32, device=dev)
+    num = torch.zeros(1, dtype=I32, device=dev)
+    call("insmos_nms_rotated", _p(boxes_sorted), n, float(thresh), int(max_keep), _p(mask), _p(keep), _p(num), _stream())
+    return keep[:int(num.item())]
+
+
+def boxes_to_voxel_units(boxes7, labels, range_min, vsize, stride):
+    boxes7 = _req(boxes7, F32, "boxes_to_voxel_units")
+    labels = _req(labels, I32, "boxes_to_voxel_units")
+    nb = boxes7.shape[0]
+    out = torch.empty((nb, 8), dtype=F32, device=boxes7.device)
+    call("insmos_boxes_to_voxel_units", _p(boxes7), _p(labels), nb, _arr(C.c_float, [float(v) for v in range_min]),
+         _arr(C.c_float, [float(v) for v in vsize]), float(stride), _p(out), _stream())
+    return out
+
+
+def box_membership(coords, boxes8, mult, out=None, out_stride=None, col_offset=0, n_class=3):
+    """Array_Index.find_features_by_bbox_with_yaw on device.  coords [n,4] (b,z,y,x) i32; boxes8 [nb,8].
+    Writes 1.0 into out[j, col_offset + label-1]; out defaults to a fresh zero [n,n_class] f32."""
+    coords = _req(coords, I32, "box_membership")
+    n = coords.shape[0]
+    dev = coords.device
+    if out is None:
+        out = torch.zeros((n, n_class), dtype=F32, device=dev)
+        out_stride, col_offset = n_class, 0
+    nb = boxes8.shape[0]
+    if nb > 0 and n > 0:
+        boxes8 = _req(boxes8, F32, "box_membership")
+        first = torch.empty(nb, dtype=I32, device=dev)
+        base = C.c_void_p(out.data_ptr() + 4 * col_offset)
+        call("insmos_box_membership", _p(coords), n, _p(boxes8), nb, float(mult), base, int(out_stride), _p(first),
+             _stream())
+    return out

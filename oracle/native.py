@@ -1,0 +1,73 @@
+"""ctypes access to oracle/native/liboracle_native.so and import helpers for oracle/_ref (test infrastructure)."""
+import ctypes as C
+import importlib.util
+import os
+
+import numpy as np
+
+from . import build
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = build.NATIVE_LIB
+        if not os.path.exists(path):
+            path = build.build_native()
+        L = C.CDLL(path)
+        L.oracle_iou_bev.restype = C.c_float
+        L.oracle_iou_bev.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_iou_matrix.restype = None
+        L.oracle_iou_matrix.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.oracle_nms.restype = C.c_int
+        L.oracle_nms.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p]
+        L.oracle_find_features_by_bbox_with_yaw.restype = None
+        L.oracle_find_features_by_bbox_with_yaw.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+def iou_matrix(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float32); b = np.ascontiguousarray(b, dtype=np.float32)
+    out = np.zeros((len(a), len(b)), dtype=np.float32)
+    lib().oracle_iou_matrix(a.ctypes.data, len(a), b.ctypes.data, len(b), out.ctypes.data)
+    return out
+
+
+def nms(boxes_sorted, thresh):
+    """boxes [n,7] sorted by descending score -> all kept indices (int64, ascending)."""
+    b = np.ascontiguousarray(boxes_sorted, dtype=np.float32)
+    keep = np.zeros(max(len(b), 1), dtype=np.int64)
+    n = lib().oracle_nms(b.ctypes.data, len(b), C.c_float(thresh), keep.ctypes.data)
+    return keep[:n]
+
+
+def find_features_by_bbox_with_yaw(vox_xyz, boxes8, n_class=3):
+    v = np.ascontiguousarray(vox_xyz, dtype=np.int32); b = np.ascontiguousarray(boxes8, dtype=np.float32)
+    out = np.zeros((len(v), n_class), dtype=np.int32)
+    lib().oracle_find_features_by_bbox_with_yaw(v.ctypes.data, len(v), b.ctypes.data, len(b), out.ctypes.data, n_class)
+    return out
+
+
+def _load_ext(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def ref_array_index():
+    """the reference's compiled Array_Index module (oracle/_ref), or None."""
+    p = build.ref_paths()[0]
+    return _load_ext("Array_Index", p) if os.path.exists(p) else None
+
+
+def ref_iou3d():
+    """the reference's compiled iou3d_nms_cuda module (oracle/_ref), or None.  Needs `import torch` first."""
+    p = build.ref_paths()[1]
+    if not os.path.exists(p):
+        return None
+    import torch  # noqa: F401  (libtorch must be loaded before the extension)
+    return _load_ext("iou3d_nms_cuda", p)

@@ -1,0 +1,165 @@
+/*
+ * oracle_native.c -- CPU restatement (plain C, fp32) of the reference's first-party native code.
+ * TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Build: oracle/build_oracle.py (gcc -O2
+ * -ffp-contract=off, no fast-math: every product and sum rounds separately, as the reference's
+ * host code compiled for baseline x86-64 does).
+ *
+ * Restated from (paths relative to the reference repository):
+ *   rotated rectangle overlap / BEV IoU   models/bbox_post_process/src/iou3d_nms_kernel.cu:34-234
+ *                                          (host twin models/bbox_post_process/src/iou3d_cpu.cpp:38-228)
+ *   64x64 suppression mask                 iou3d_nms_kernel.cu:267-311
+ *   greedy sweep                           models/bbox_post_process/src/iou3d_nms.cpp:118-132
+ *   voxel-in-box membership                models/utils/src/Array_Index.cpp:14-79
+ * Pinned against the compiled reference by tests/test_oracle_native.py.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct { float x, y; } pt;
+
+static float cross_o(pt p1, pt p2, pt p0) {            /* iou3d_nms_kernel.cu:38-40 */
+    return (p1.x - p0.x) * (p2.y - p0.y) - (p2.x - p0.x) * (p1.y - p0.y);
+}
+static float cross_v(pt a, pt b) { return a.x * b.y - a.y * b.x; }   /* :34-36 */
+static float fmin2(float a, float b) { return a < b ? a : b; }
+static float fmax2(float a, float b) { return a > b ? a : b; }
+
+static int rect_cross(pt p1, pt p2, pt q1, pt q2) {    /* :42-48 */
+    return fmin2(p1.x, p2.x) <= fmax2(q1.x, q2.x) && fmin2(q1.x, q2.x) <= fmax2(p1.x, p2.x) &&
+           fmin2(p1.y, p2.y) <= fmax2(q1.y, q2.y) && fmin2(q1.y, q2.y) <= fmax2(p1.y, p2.y);
+}
+
+static int in_box2d(const float* box, pt p) {          /* :50-60, MARGIN 1e-2 */
+    const float margin = 1e-2f;
+    float cx = box[0], cy = box[1];
+    float ac = cosf(-box[6]), as = sinf(-box[6]);
+    float rx = (p.x - cx) * ac + (p.y - cy) * (-as);
+    float ry = (p.x - cx) * as + (p.y - cy) * ac;
+    return fabsf(rx) < box[3] / 2 + margin && fabsf(ry) < box[4] / 2 + margin;
+}
+
+static int seg_x(pt p1, pt p0, pt q1, pt q0, pt* ans) {   /* :62-93 */
+    if (!rect_cross(p0, p1, q0, q1)) return 0;
+    float s1 = cross_o(q0, p1, p0), s2 = cross_o(p1, q1, p0);
+    float s3 = cross_o(p0, q1, q0), s4 = cross_o(q1, p1, q0);
+    if (!(s1 * s2 > 0 && s3 * s4 > 0)) return 0;
+    float s5 = cross_o(q1, p1, p0);
+    if (fabsf(s5 - s1) > 1e-8f) {
+        ans->x = (s5 * q0.x - s1 * q1.x) / (s5 - s1);
+        ans->y = (s5 * q0.y - s1 * q1.y) / (s5 - s1);
+    } else {
+        float a0 = p0.y - p1.y, b0 = p1.x - p0.x, c0 = p0.x * p1.y - p1.x * p0.y;
+        float a1 = q0.y - q1.y, b1 = q1.x - q0.x, c1 = q0.x * q1.y - q1.x * q0.y;
+        float D = a0 * b1 - a1 * b0;
+        ans->x = (b0 * c1 - b1 * c0) / D;
+        ans->y = (a1 * c0 - a0 * c1) / D;
+    }
+    return 1;
+}
+
+static void corners(const float* b, pt c[5]) {          /* :108-150 */
+    float hx = b[3] / 2, hy = b[4] / 2;
+    float x1 = b[0] - hx, y1 = b[1] - hy, x2 = b[0] + hx, y2 = b[1] + hy;
+    float ca = cosf(b[6]), sa = sinf(b[6]);
+    float px[4] = {x1, x2, x2, x1}, py[4] = {y1, y1, y2, y2};
+    for (int k = 0; k < 4; ++k) {                      /* rotate_around_center :95-99 */
+        c[k].x = (px[k] - b[0]) * ca + (py[k] - b[1]) * (-sa) + b[0];
+        c[k].y = (px[k] - b[0]) * sa + (py[k] - b[1]) * ca + b[1];
+    }
+    c[4] = c[0];
+}
+
+float oracle_box_overlap(const float* A, const float* B) {   /* :104-225 */
+    pt ca[5], cb[5], pts[16], ctr = {0.f, 0.f};
+    corners(A, ca); corners(B, cb);
+    int cnt = 0;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            pt x;
+            if (seg_x(ca[i + 1], ca[i], cb[j + 1], cb[j], &x)) { ctr.x += x.x; ctr.y += x.y; pts[cnt++] = x; }
+        }
+    for (int k = 0; k < 4; ++k) {
+        if (in_box2d(A, cb[k])) { ctr.x += cb[k].x; ctr.y += cb[k].y; pts[cnt++] = cb[k]; }
+        if (in_box2d(B, ca[k])) { ctr.x += ca[k].x; ctr.y += ca[k].y; pts[cnt++] = ca[k]; }
+    }
+    ctr.x /= cnt; ctr.y /= cnt;
+    for (int j = 0; j < cnt - 1; ++j)                   /* bubble sort by angle :196-207 */
+        for (int i = 0; i < cnt - j - 1; ++i)
+            if (atan2f(pts[i].y - ctr.y, pts[i].x - ctr.x) > atan2f(pts[i + 1].y - ctr.y, pts[i + 1].x - ctr.x)) {
+                pt t = pts[i]; pts[i] = pts[i + 1]; pts[i + 1] = t;
+            }
+    float area = 0.f;
+    for (int k = 0; k < cnt - 1; ++k) {
+        pt u = {pts[k].x - pts[0].x, pts[k].y - pts[0].y}, v = {pts[k + 1].x - pts[0].x, pts[k + 1].y - pts[0].y};
+        area += cross_v(u, v);
+    }
+    return fabsf(area) / 2.0f;
+}
+
+float oracle_iou_bev(const float* A, const float* B) {       /* :227-234 */
+    float sa = A[3] * A[4], sb = B[3] * B[4];
+    float so = oracle_box_overlap(A, B);
+    return so / fmaxf(sa + sb - so, 1e-8f);
+}
+
+void oracle_iou_matrix(const float* a, int na, const float* b, int nb, float* out) {
+    for (int i = 0; i < na; ++i)
+        for (int j = 0; j < nb; ++j) out[(size_t)i * nb + j] = oracle_iou_bev(a + i * 7, b + j * 7);
+}
+
+/* nms_gpu: boxes sorted by descending score.  keep[] gets ALL kept indices (ascending); returns count. */
+int oracle_nms(const float* boxes, int n, float thresh, int64_t* keep) {
+    const int cb = (n + 63) / 64;
+    uint64_t* mask = (uint64_t*)calloc((size_t)n * cb + 1, sizeof(uint64_t));
+    for (int i = 0; i < n; ++i)                           /* nms_kernel :267-311 */
+        for (int c = i / 64; c < cb; ++c) {
+            uint64_t t = 0;
+            int start = (c == i / 64) ? (i % 64) + 1 : 0;
+            int ncol = n - c * 64 < 64 ? n - c * 64 : 64;
+            for (int j = start; j < ncol; ++j)
+                if (oracle_iou_bev(boxes + (size_t)i * 7, boxes + (size_t)(c * 64 + j) * 7) > thresh) t |= 1ull << j;
+            mask[(size_t)i * cb + c] = t;
+        }
+    uint64_t* remv = (uint64_t*)calloc(cb + 1, sizeof(uint64_t));
+    int num = 0;
+    for (int i = 0; i < n; ++i) {                         /* iou3d_nms.cpp:118-132 */
+        int nb = i / 64, ib = i % 64;
+        if (!(remv[nb] & (1ull << ib))) {
+            keep[num++] = i;
+            const uint64_t* p = mask + (size_t)i * cb;
+            for (int j = nb; j < cb; ++j) remv[j] |= p[j];
+        }
+    }
+    free(mask); free(remv);
+    return num;
+}
+
+/* Array_Index.find_features_by_bbox_with_yaw: vox [n,3] (x,y,z) int32, boxes [nb,8] float, out [n,ncls] int32 */
+void oracle_find_features_by_bbox_with_yaw(const int32_t* vox, int n, const float* boxes, int nb, int32_t* out, int ncls) {
+    for (int i = 0; i < nb; ++i) {
+        const float* b = boxes + (size_t)i * 8;
+        float center[3] = {b[0], b[1], b[2]}, extend[3] = {b[3], b[4], b[5]};
+        float theta = b[6];
+        float cos_theta = cosf(theta), sin_theta = sinf(theta);
+        int first_flag = 0, first_point[3] = {0, 0, 0};
+        for (int j = 0; j < n; ++j) {
+            const int32_t* r = vox + (size_t)j * 3;
+            if (first_flag == 1 &&
+                (r[0] > (first_point[0] + extend[0]) || r[0] < (first_point[0] - extend[0]) ||
+                 r[1] > (first_point[1] + extend[1]) || r[1] < (first_point[1] - extend[1]) ||
+                 r[2] > (first_point[2] + extend[2]) || r[2] < (first_point[2] - extend[2])))
+                continue;
+            float centered[3] = {r[0] - center[0], r[1] - center[1], r[2] - center[2]};
+            float rx = centered[0] * cos_theta + centered[1] * sin_theta;
+            float ry = -centered[0] * sin_theta + centered[1] * cos_theta;
+            if (rx <= extend[0] / 2 && rx >= -extend[0] / 2 && ry <= extend[1] / 2 && ry >= -extend[1] / 2 &&
+                centered[2] <= extend[2] / 2 && centered[2] >= -extend[2] / 2) {
+                int label = (int)b[7];
+                if (label > 0 && label <= ncls) out[(size_t)j * ncls + label - 1] = 1;
+                if (!first_flag) { first_flag = 1; first_point[0] = r[0]; first_point[1] = r[1]; first_point[2] = r[2]; }
+            }
+        }
+    }
+}
