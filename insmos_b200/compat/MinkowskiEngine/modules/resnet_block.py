@@ -1,0 +1,65 @@
+"""MinkowskiEngine.modules.resnet_block: BasicBlock / Bottleneck (resnet.py:96-126 builds them).
+
+Same sub-module names as upstream (conv1, norm1, conv2, norm2[, conv3, norm3], downsample) so that
+state_dict keys match.  In eval mode BatchNorm, ReLU and the residual add are fused into the
+convolution epilogues; in training mode the plain op sequence runs.
+"""
+import torch.nn as nn
+
+import MinkowskiEngine as ME
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, dilation=1, downsample=None, bn_momentum=0.1, dimension=-1):
+        super().__init__()
+        assert dimension > 0
+        self.conv1 = ME.MinkowskiConvolution(inplanes, planes, kernel_size=3, stride=stride, dilation=dilation,
+                                             dimension=dimension)
+        self.norm1 = ME.MinkowskiBatchNorm(planes, momentum=bn_momentum)
+        self.conv2 = ME.MinkowskiConvolution(planes, planes, kernel_size=3, stride=1, dilation=dilation,
+                                             dimension=dimension)
+        self.norm2 = ME.MinkowskiBatchNorm(planes, momentum=bn_momentum)
+        self.relu = ME.MinkowskiReLU(inplace=True)
+        self.downsample = downsample
+
+    def forward(self, x):
+        if self.training:
+            out = self.relu(self.norm1(self.conv1(x)))
+            out = self.norm2(self.conv2(out))
+            res = x if self.downsample is None else self.downsample(x)
+            return self.relu(out._like(out.F + res.F))
+        out = self.conv1(x, bn=self.norm1, relu=True)
+        if self.downsample is None:
+            res = x
+        elif isinstance(self.downsample, nn.Sequential) and len(self.downsample) == 2 and \
+                isinstance(self.downsample[1], ME.MinkowskiBatchNorm):
+            res = self.downsample[0](x, bn=self.downsample[1])
+        else:
+            res = self.downsample(x)
+        return self.conv2(out, bn=self.norm2, residual=res.F, relu=True)
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, dilation=1, downsample=None, bn_momentum=0.1, dimension=-1):
+        super().__init__()
+        assert dimension > 0
+        self.conv1 = ME.MinkowskiConvolution(inplanes, planes, kernel_size=1, dimension=dimension)
+        self.norm1 = ME.MinkowskiBatchNorm(planes, momentum=bn_momentum)
+        self.conv2 = ME.MinkowskiConvolution(planes, planes, kernel_size=3, stride=stride, dilation=dilation,
+                                             dimension=dimension)
+        self.norm2 = ME.MinkowskiBatchNorm(planes, momentum=bn_momentum)
+        self.conv3 = ME.MinkowskiConvolution(planes, planes * self.expansion, kernel_size=1, dimension=dimension)
+        self.norm3 = ME.MinkowskiBatchNorm(planes * self.expansion, momentum=bn_momentum)
+        self.relu = ME.MinkowskiReLU(inplace=True)
+        self.downsample = downsample
+
+    def forward(self, x):
+        out = self.relu(self.norm1(self.conv1(x)))
+        out = self.relu(self.norm2(self.conv2(out)))
+        out = self.norm3(self.conv3(out))
+        res = x if self.downsample is None else self.downsample(x)
+        return self.relu(out._like(out.F + res.F))

@@ -1,0 +1,115 @@
+import math
+
+import torch
+import torch.nn as nn
+
+from insmos_b200 import ops
+
+from .core import IndiceData, SparseConvTensor
+from .modules import SparseModule
+
+
+def _tup3(v):
+    return tuple(int(x) for x in v) if isinstance(v, (list, tuple)) else (int(v),) * 3
+
+
+def fold_bn(bn):
+    """eval-mode BatchNorm1d as (scale, shift), cached on the module until a parameter changes."""
+    ver = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
+           bn.weight.data_ptr(), bn.running_mean.data_ptr())
+    cache = getattr(bn, "_insmos_folded", None)
+    if cache is None or cache[0] != ver:
+        with torch.no_grad():
+            scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            shift = bn.bias - bn.running_mean * scale
+        cache = (ver, scale.contiguous(), shift.contiguous())
+        bn._insmos_folded = cache
+    return cache[1], cache[2]
+
+
+class SparseConvolution(SparseModule):
+    def __init__(self, ndim, in_channels, out_channels, kernel_size=3, stride=1, padding=0, dilation=1, groups=1,
+                 bias=True, subm=False, output_padding=0, transposed=False, inverse=False, indice_key=None,
+                 algo=None, **kwargs):
+        super().__init__()
+        assert ndim == 3 and groups == 1
+        self.ndim, self.in_channels, self.out_channels = ndim, in_channels, out_channels
+        self.kernel_size, self.stride, self.padding = _tup3(kernel_size), _tup3(stride), _tup3(padding)
+        if _tup3(dilation) != (1, 1, 1) or transposed:
+            raise NotImplementedError("dilation / transposed SparseConvolution are not on the InsMOS path")
+        self.subm, self.inverse, self.indice_key = subm, inverse, indice_key
+        self.weight = nn.Parameter(torch.empty(out_channels, *self.kernel_size, in_channels))
+        self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
+        self._wk = None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        with torch.no_grad():
+            fan_in = self.in_channels * math.prod(self.kernel_size)
+            nn.init.kaiming_uniform_(self.weight.view(self.out_channels, -1), a=math.sqrt(5))
+            if self.bias is not None:
+                b = 1 / math.sqrt(fan_in)
+                self.bias.uniform_(-b, b)
+
+    def kernel_major_weight(self):
+        """[K, Cin, Cout] view of the spconv-layout weight, cached until the parameter changes."""
+        ver = (self.weight._version, self.weight.data_ptr())
+        if self._wk is None or self._wk[0] != ver:
+            with torch.no_grad():
+                wk = self.weight.reshape(self.out_channels, -1, self.in_channels).permute(1, 2, 0).contiguous()
+            self._wk = (ver, wk)
+        return self._wk[1]
+
+    def forward(self, x, bn=None, relu=False, residual=None, algo=0):
+        assert isinstance(x, SparseConvTensor)
+        scale = shift = None
+        if bn is not None:
+            scale, shift = fold_bn(bn)
+        data = x.find_indice_pair(self.indice_key)
+        if self.inverse:
+            if data is None:
+                raise RuntimeError("SparseInverseConv3d: indice_key %r not found" % (self.indice_key,))
+            rb = data.inverse_rulebook()
+            out_set, out_shape = data.in_set, data.in_shape
+        elif self.subm:
+            if data is None or data.in_set is not x.coordset:
+                data = IndiceData(x.coordset, x.coordset, self.kernel_size, (1, 1, 1), self.padding, x.spatial_shape,
+                                  x.spatial_shape, True)
+                if self.indice_key is not None:
+                    x.indice_dict[self.indice_key] = data
+            rb = data.forward_rulebook()
+            out_set, out_shape = data.out_set, x.spatial_shape
+        else:
+            if data is None or data.in_set is not x.coordset:
+                out_shape = [(i + 2 * p - k) // s + 1 for i, k, s, p in
+                             zip(x.spatial_shape, self.kernel_size, self.stride, self.padding)]
+                out_set = ops.spconv_out_coords(x.coordset, self.kernel_size, self.stride, self.padding, out_shape)
+                data = IndiceData(x.coordset, out_set, self.kernel_size, self.stride, self.padding, x.spatial_shape,
+                                  out_shape, False)
+                if self.indice_key is not None:
+                    x.indice_dict[self.indice_key] = data
+            rb = data.forward_rulebook()
+            out_set, out_shape = data.out_set, data.out_shape
+        f = ops.sparse_conv(x.features, self.kernel_major_weight(), rb, scale=scale, shift=shift, bias=self.bias,
+                            residual=residual, relu=relu, algo=algo)
+        return SparseConvTensor(f, out_set.coords, out_shape, x.batch_size, indice_dict=x.indice_dict,
+                                benchmark=x.benchmark, coordset=out_set)
+
+
+class SubMConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None, algo=None, **kwargs):
+        super().__init__(3, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, subm=True,
+                         indice_key=indice_key)
+
+
+class SparseConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None, algo=None, **kwargs):
+        super().__init__(3, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias,
+                         indice_key=indice_key)
+
+
+class SparseInverseConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, indice_key=None, bias=True, algo=None, **kwargs):
+        super().__init__(3, in_channels, out_channels, kernel_size, bias=bias, inverse=True, indice_key=indice_key)

@@ -199,7 +199,7 @@ extern "C" int insmos_sparse_conv_fwd(const float* in, int64_t n_in, int32_t Cin
                                       const uint16_t* seg, const uint32_t* entries, int32_t TM,
                                       float* out, int64_t n_out,
                                       const insmos_epilogue_t* ep_in, int32_t algo, void* stream) {
-    if (!in || !weight || !seg || !entries || !out || Cin <= 0 || Cout <= 0 || K <= 0 || n_out < 0 || n_in < 0)
+    if ((n_in > 0 && !in) || !weight || !seg || !entries || (n_out > 0 && !out) || Cin <= 0 || Cout <= 0 || K <= 0 || n_out < 0 || n_in < 0)
         return INSMOS_ERR_INVALID_ARG;
     if (TM != 16 && TM != 32 && TM != 64 && TM != 128) return INSMOS_ERR_INVALID_ARG;
     if (n_in > (int64_t)INSMOS_ROW_MASK + 1) return INSMOS_ERR_UNSUPPORTED;

@@ -232,7 +232,7 @@ extern "C" int insmos_voxelize4d(const float* points, int64_t n, int32_t point_s
                                  insmos_slot_t* table, int64_t cap, int32_t* slot_of_point,
                                  int32_t* out_coords, int32_t* inverse, int32_t* cur_index,
                                  int32_t* counters, void* scratch, void* stream) {
-    if (!points || point_stride < 5 || !quant || !out_coords || !inverse) return INSMOS_ERR_INVALID_ARG;
+    if ((n > 0 && !points) || point_stride < 5 || !quant || !out_coords || !inverse) return INSMOS_ERR_INVALID_ARG;
     Src4D src{points, point_stride, quant[0], quant[1], quant[2], quant[3]};
     return run_unique(src, n, table, cap, slot_of_point, out_coords, inverse, cur_index, counters, scratch, INT_MAX,
                       (cudaStream_t)stream);
@@ -242,7 +242,7 @@ extern "C" int insmos_unique_coords(const int32_t* coords, int64_t n, int32_t nc
                                     insmos_slot_t* table, int64_t cap, int32_t* slot_of_point,
                                     int32_t* out_coords, int32_t* inverse,
                                     int32_t* counters, void* scratch, void* stream) {
-    if (!coords || (ncol != 4 && ncol != 5) || !out_coords) return INSMOS_ERR_INVALID_ARG;
+    if ((n > 0 && !coords) || (ncol != 4 && ncol != 5) || !out_coords) return INSMOS_ERR_INVALID_ARG;
     SrcInt src{coords, ncol, 1, 1, 1, 1};
     if (q) { src.q0 = q[0]; src.q1 = q[1]; src.q2 = q[2]; src.q3 = (ncol > 4) ? q[3] : 1; }
     if (src.q0 < 1 || src.q1 < 1 || src.q2 < 1 || src.q3 < 1) return INSMOS_ERR_INVALID_ARG;
@@ -260,7 +260,7 @@ extern "C" int insmos_spconv_out_coords(const int32_t* in_coords, int64_t n,
                                         const int32_t* out_shape,
                                         insmos_slot_t* table, int64_t cap,
                                         int32_t* out_coords, int32_t* counters, void* scratch, void* stream) {
-    if (!in_coords || !ksize || !stride || !pad || !out_shape || !out_coords) return INSMOS_ERR_INVALID_ARG;
+    if ((n > 0 && !in_coords) || !ksize || !stride || !pad || !out_shape || !out_coords) return INSMOS_ERR_INVALID_ARG;
     const int K = ksize[0] * ksize[1] * ksize[2];
     if (K <= 0 || stride[0] < 1 || stride[1] < 1 || stride[2] < 1) return INSMOS_ERR_INVALID_ARG;
     SrcSpOut src{in_coords, K, ksize[0], ksize[1], ksize[2], stride[0], stride[1], stride[2],
@@ -329,7 +329,7 @@ extern "C" int insmos_voxelize3d(const float* points, int64_t n, int32_t C,
                                  int32_t* coords, int32_t* num_points, float* voxels, float* mean,
                                  int32_t* pc_voxel_id, int32_t* work,
                                  int32_t* counters, void* scratch, void* stream) {
-    if (!points || C < 3 || !range || !vsize || !grid || max_voxels <= 0 || max_points <= 0 || !coords || !num_points ||
+    if ((n > 0 && !points) || C < 3 || !range || !vsize || !grid || max_voxels <= 0 || max_points <= 0 || !coords || !num_points ||
         !mean || !pc_voxel_id || !work)
         return INSMOS_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;

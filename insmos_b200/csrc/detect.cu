@@ -168,13 +168,11 @@ k_nms_sweep(const unsigned long long* __restrict__ mask, int n, int max_keep, in
     __shared__ unsigned long long s_kept;
     __shared__ int s_num;
     const int tid = threadIdx.x;
-    unsigned long long remv = 0ull;                               // thread j owns removal words j, j+64, ...
     // col_blocks <= 64 for n <= 4096; larger n handled by striding words over threads
     if (tid == 0) s_num = 0;
     __syncthreads();
     // per-thread removal words for columns tid + 64*w are kept in a small local array
     unsigned long long remv_w[4] = {0ull, 0ull, 0ull, 0ull};     // supports n <= 16384
-    (void)remv;
     for (int blk = 0; blk < col_blocks; ++blk) {
         const int base = blk * 64;
         const int cnt = min(64, n - base);
@@ -215,7 +213,7 @@ k_nms_sweep(const unsigned long long* __restrict__ mask, int n, int max_keep, in
 
 extern "C" int insmos_nms_rotated(const float* boxes, int32_t n, float thresh, int32_t max_keep,
                                   unsigned long long* mask, int32_t* keep, int32_t* num_keep, void* stream) {
-    if (!boxes || !mask || !keep || !num_keep || n < 0 || max_keep <= 0) return INSMOS_ERR_INVALID_ARG;
+    if ((n > 0 && !boxes) || !mask || !keep || !num_keep || n < 0 || max_keep <= 0) return INSMOS_ERR_INVALID_ARG;
     if (n > 16384) return INSMOS_ERR_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { INSMOS_CHECK_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int32_t), st)); return INSMOS_OK; }

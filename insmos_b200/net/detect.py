@@ -1,0 +1,55 @@
+"""Detection post-processing (a10) and instance-feature fusion helpers (a11) on device.
+
+Mirrors models/post_process.py:5-24,112-224, models/bbox_post_process/iou3d_nms_utils.py:64-79 and the
+call sites of Array_Index.find_features_by_bbox_with_yaw in models/backbones_3d/spconv_unet.py:319-401.
+Selection order follows the reference: score >= thresh, top-k (<= NMS_PRE_MAXSIZE) by score, sort
+descending, rotated NMS (device-side sweep), first NMS_POST_MAXSIZE.
+"""
+import torch
+
+from insmos_b200 import ops
+
+
+def class_agnostic_nms(scores, boxes, nms_config, score_thresh):
+    """returns indices (int64, into the unfiltered arrays) of the selected boxes, in NMS order."""
+    cand = torch.nonzero(scores >= score_thresh).view(-1)              # one host sync (data-dependent size)
+    if cand.numel() == 0:
+        return cand
+    s = scores[cand]
+    k = min(int(nms_config["NMS_PRE_MAXSIZE"]), s.shape[0])
+    top_s, top_i = torch.topk(s, k=k)
+    order = top_s.sort(0, descending=True)[1]                          # iou3d_nms_utils.py:72 sorts again
+    b = boxes[cand[top_i[order]]][:, 0:7].contiguous()
+    keep = ops.nms_rotated(b, float(nms_config["NMS_THRESH"]), int(nms_config["NMS_POST_MAXSIZE"]))
+    return cand[top_i[order[keep.long()]]]
+
+
+def post_processing(batch_dict, cfg, num_class):
+    """test/eval-mode post_processing for batch 1 -> ([{'pred_boxes','pred_scores','pred_labels'}], {})"""
+    boxes, scores, labels = batch_dict["_decoded"]
+    if cfg["NMS_CONFIG"]["MULTI_CLASSES_NMS"]:
+        raise NotImplementedError("MULTI_CLASSES_NMS is disabled in the reference config (config.yaml:152)")
+    sel = class_agnostic_nms(scores, boxes, cfg["NMS_CONFIG"], cfg["SCORE_THRESH"])
+    final_scores = scores[sel]
+    if cfg.get("OUTPUT_RAW_SCORE", False):
+        final_scores = batch_dict["batch_cls_preds"][0].max(dim=-1)[0][sel]
+    rec = {"pred_boxes": boxes[sel], "pred_scores": final_scores, "pred_labels": labels[sel].long()}
+    return [rec], {}
+
+
+class InstanceBoxes:
+    """the NMS survivors in voxel units of the stride-8 level; `bits(indices, level_mult)` is the
+    device-side Array_Index.find_features_by_bbox_with_yaw for one resolution level."""
+
+    def __init__(self, pred, range_min, voxel_size, stride, num_class):
+        self.num_class = num_class
+        b7 = pred["pred_boxes"].contiguous()
+        self.nb = b7.shape[0]
+        self.boxes8 = ops.boxes_to_voxel_units(b7, pred["pred_labels"].to(torch.int32).contiguous(), range_min, voxel_size,
+                                               float(stride)) if self.nb else torch.zeros((0, 8), device=b7.device)
+
+    def concat_bits(self, features, indices, mult):
+        """cat([features, one-hot class membership], dim=1) for the voxels `indices` [n,4] (b,z,y,x)."""
+        n, c = features.shape
+        bits = ops.box_membership(indices, self.boxes8, float(mult), n_class=self.num_class)
+        return ops.concat2(features, bits), bits

@@ -1,0 +1,124 @@
+"""CUDA feature kernels vs the oracle (fp32, tolerance written per test)."""
+import numpy as np
+import pytest
+import torch
+
+from insmos_b200 import ops, synth
+from oracle import me, sp
+
+pytestmark = pytest.mark.gpu
+
+# sparse-conv tolerance: fp32 accumulation in a different order than the oracle (k-major sgemm);
+# both SIMT fp32 and 3xTF32 tensor-core paths must meet it.
+RTOL, ATOL = 2e-5, 2e-5
+
+
+def _setup(cuda, ksize, seed=7):
+    pts = synth.make_sequence(seed=seed, n_scans=3, n_elev=32, n_azim=400)
+    cs, _, _ = ops.voxelize4d(torch.from_numpy(pts).to(cuda), [0.1, 0.1, 0.1, 0.1])
+    c = cs.coords.cpu().numpy()
+    maps = me.kernel_map(c, c, ksize, [1, 1, 1, 1])
+    rb = ops.build_rulebook(cs, cs, ops.spec_me_cube(ksize, [1, 1, 1, 1]))
+    return cs, c, maps, rb
+
+
+@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("Cin,Cout", [(1, 8), (8, 8), (16, 8), (24, 16), (48, 32), (7, 16), (19, 16), (131, 128), (64, 64)])
+def test_sparse_conv_matches_oracle(cuda, algo, Cin, Cout):
+    cs, c, maps, rb = _setup(cuda, [3, 3, 3, 3])
+    g = torch.Generator().manual_seed(Cin * 1000 + Cout)
+    feats = torch.randn((len(c), Cin), generator=g)
+    W = torch.randn((81, Cin, Cout), generator=g) / np.sqrt(Cin * 20.0)
+    ref = me.conv(feats, W, maps, len(c))
+    out = ops.sparse_conv(feats.to(cuda), W.to(cuda), rb, algo=algo).cpu()
+    err = (out - ref).abs().max().item()
+    assert torch.allclose(out, ref, rtol=RTOL, atol=ATOL), "max abs err %.3e (ref max %.3f)" % (err, ref.abs().max())
+
+
+@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("TM", [16, 32, 64, 128])
+def test_sparse_conv_tile_sizes_and_epilogue(cuda, algo, TM):
+    cs, c, maps, _ = _setup(cuda, [3, 3, 3, 3])
+    rb = ops.build_rulebook(cs, cs, ops.spec_me_cube([3, 3, 3, 3], [1, 1, 1, 1]), TM=TM)
+    g = torch.Generator().manual_seed(TM)
+    Cin, Cout = 16, 24
+    feats = torch.randn((len(c), Cin), generator=g)
+    W = torch.randn((81, Cin, Cout), generator=g) / 18.0
+    scale, shift = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g)
+    res = torch.randn((len(c), Cout), generator=g)
+    ref = torch.relu(me.conv(feats, W, maps, len(c)) * scale + shift + res)
+    out = ops.sparse_conv(feats.to(cuda), W.to(cuda), rb, scale=scale.to(cuda), shift=shift.to(cuda),
+                          residual=res.to(cuda), relu=True, algo=algo).cpu()
+    assert torch.allclose(out, ref, rtol=RTOL, atol=ATOL), (out - ref).abs().max()
+
+
+def test_conv0_125_offsets_single_channel(cuda):
+    cs, c, maps, rb = _setup(cuda, [5, 5, 5, 1])
+    g = torch.Generator().manual_seed(3)
+    feats = torch.full((len(c), 1), 0.5)
+    W = torch.randn((125, 1, 8), generator=g)
+    ref = me.conv(feats, W, maps, len(c))
+    for algo in (0, 1, 2):
+        out = ops.sparse_conv(feats.to(cuda), W.to(cuda), rb, algo=algo).cpu()
+        assert torch.allclose(out, ref, rtol=RTOL, atol=ATOL)
+
+
+def test_strided_and_transposed_conv(cuda):
+    cs, c, _, _ = _setup(cuda, [3, 3, 3, 3])
+    co, _ = me.stride_coords(c, [2, 2, 2, 1])
+    cg, _ = ops.unique_coords(cs.coords, q=[2, 2, 2, 1])
+    maps = me.kernel_map(c, co, [2, 2, 2, 1], [1, 1, 1, 1])
+    g = torch.Generator().manual_seed(11)
+    feats = torch.randn((len(c), 8), generator=g)
+    W = torch.randn((8, 8, 16), generator=g) / 4.0
+    rb = ops.build_rulebook(cg, cs, ops.spec_me_cube([2, 2, 2, 1], [1, 1, 1, 1]))
+    ref = me.conv(feats, W, maps, len(co))
+    for algo in (1, 2):
+        assert torch.allclose(ops.sparse_conv(feats.to(cuda), W.to(cuda), rb, algo=algo).cpu(), ref, rtol=RTOL, atol=ATOL)
+    Wt = torch.randn((8, 16, 8), generator=g) / 4.0
+    rbt = ops.build_rulebook(cs, cg, ops.spec_me_up([2, 2, 2, 1], [2, 2, 2, 1], [1, 1, 1, 1]))
+    reft = me.conv(ref, Wt, me.transpose_map(maps), len(c))
+    for algo in (1, 2):
+        assert torch.allclose(ops.sparse_conv(ref.to(cuda), Wt.to(cuda), rbt, algo=algo).cpu(), reft, rtol=RTOL, atol=ATOL)
+
+
+def test_linear_affine_concat_pairsum_gather_segment_mean(cuda):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((5000, 48), generator=g)
+    W = torch.randn((48, 32), generator=g) / 7.0
+    b = torch.randn(32, generator=g)
+    res = torch.randn((5000, 32), generator=g)
+    out = ops.linear(x.to(cuda), W.to(cuda), bias=b.to(cuda), residual=res.to(cuda), relu=True).cpu()
+    assert torch.allclose(out, torch.relu(x @ W + b + res), rtol=1e-5, atol=1e-5)
+    s, t = torch.rand(48, generator=g) + 0.5, torch.randn(48, generator=g)
+    assert torch.allclose(ops.affine_act(x.to(cuda), scale=s.to(cuda), shift=t.to(cuda), relu=True).cpu(),
+                          torch.relu(x * s + t), rtol=1e-6, atol=1e-6)
+    y = torch.randn((5000, 3), generator=g)
+    assert torch.equal(ops.concat2(x.to(cuda), y.to(cuda)).cpu(), torch.cat([x, y], 1))
+    a = torch.randn((5000, 24), generator=g)
+    assert torch.allclose(ops.pairsum_add(a.to(cuda), x.to(cuda)).cpu(), a + x.view(5000, 24, 2).sum(2), atol=1e-6)
+    idx = torch.randint(-1, 5000, (7000,), generator=g).to(torch.int32)
+    gat = ops.gather_rows(x.to(cuda), idx.to(cuda)).cpu()
+    assert torch.equal(gat, sp.gather_features_by_pc_voxel_id(x, idx.numpy()))
+    inv = torch.randint(0, 900, (5000,), generator=g).to(torch.int32)
+    assert torch.allclose(ops.segment_mean(x.to(cuda), inv.to(cuda), 900).cpu(), me.segment_mean(x, inv.numpy(), 900),
+                          rtol=1e-5, atol=1e-5)
+    half = torch.full((5000, 1), 0.5)
+    assert torch.equal(ops.segment_mean(half.to(cuda), inv.to(cuda), 900).cpu(), me.segment_mean(half, inv.numpy(), 900))
+
+
+def test_dense_scatter_and_current_points(cuda):
+    g = torch.Generator().manual_seed(6)
+    zyx = torch.stack([torch.randint(0, 2, (3000,), generator=g), torch.randint(0, 125, (3000,), generator=g),
+                       torch.randint(0, 150, (3000,), generator=g)], 1)
+    zyx = torch.unique(zyx, dim=0)
+    ind = torch.cat([torch.zeros((len(zyx), 1), dtype=torch.long), zyx], 1).to(torch.int32)
+    f = torch.randn((len(ind), 128), generator=g)
+    d = ops.dense_scatter(f.to(cuda), ind.to(cuda), 2, 125, 150).cpu()
+    assert torch.equal(d, sp.dense(f, ind.numpy(), [2, 125, 150])[0])
+    pts = torch.randn((1000, 5), generator=g)
+    cur = torch.arange(0, 1000, 3, dtype=torch.int32)
+    inv = torch.randint(0, 50, (1000,), generator=g).to(torch.int32)
+    vf = torch.randn((50, 3), generator=g)
+    out = ops.build_current_points(pts.to(cuda), cur.to(cuda), inv.to(cuda), vf.to(cuda), 3).cpu()
+    assert torch.equal(out, torch.hstack([pts[cur.long(), :4], vf[inv[cur.long()].long()]]))

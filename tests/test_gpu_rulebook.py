@@ -1,0 +1,67 @@
+"""CUDA rule books vs the oracle's kernel maps -- bit exact after canonical sort (SURVEY 8d parity gate)."""
+import numpy as np
+import pytest
+import torch
+
+from insmos_b200 import ops, synth
+from oracle import me, sp
+
+pytestmark = pytest.mark.gpu
+
+
+def _levels(cuda, seed=5, n_scans=4, n_elev=32, n_azim=500):
+    pts = synth.make_sequence(seed=seed, n_scans=n_scans, n_elev=n_elev, n_azim=n_azim)
+    cs, _, _ = ops.voxelize4d(torch.from_numpy(pts).to(cuda), [0.1, 0.1, 0.1, 0.1])
+    return cs, cs.coords.cpu().numpy()
+
+
+def _check(rb, maps, n_in, n_out):
+    got = rb.to_coo().numpy()
+    exp = me.maps_to_triples(maps, n_in, n_out)
+    assert rb.num_pairs == len(exp), "pair count %d vs oracle %d" % (rb.num_pairs, len(exp))
+    assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("ksize", [[3, 3, 3, 3], [5, 5, 5, 1]])
+@pytest.mark.parametrize("TM", [None, 16, 128])
+def test_me_cube_maps(cuda, ksize, TM):
+    cs, c = _levels(cuda)
+    rb = ops.build_rulebook(cs, cs, ops.spec_me_cube(ksize, [1, 1, 1, 1]), TM=TM)
+    _check(rb, me.kernel_map(c, c, ksize, [1, 1, 1, 1]), len(c), len(c))
+
+
+def test_me_strided_and_transposed_maps_all_levels(cuda):
+    cs, c = _levels(cuda)
+    fine_g, fine_o, ts = cs, c, 1
+    for _ in range(3):
+        coarse_o, _ = me.stride_coords(fine_o, [2 * ts, 2 * ts, 2 * ts, 1])
+        coarse_g, _ = ops.unique_coords(fine_g.coords, q=[2 * ts, 2 * ts, 2 * ts, 1])
+        maps = me.kernel_map(fine_o, coarse_o, [2, 2, 2, 1], [ts, ts, ts, 1])
+        rb = ops.build_rulebook(coarse_g, fine_g, ops.spec_me_cube([2, 2, 2, 1], [ts, ts, ts, 1]))
+        _check(rb, maps, len(fine_o), len(coarse_o))
+        rbt = ops.build_rulebook(fine_g, coarse_g, ops.spec_me_up([2, 2, 2, 1], [2, 2, 2, 1], [ts, ts, ts, 1]))
+        _check(rbt, me.transpose_map(maps), len(coarse_o), len(fine_o))
+        # 3^4 map at the coarse level (offsets scaled by the tensor stride, time stride stays 1)
+        ts2 = 2 * ts
+        rb3 = ops.build_rulebook(coarse_g, coarse_g, ops.spec_me_cube([3, 3, 3, 3], [ts2, ts2, ts2, 1]))
+        _check(rb3, me.kernel_map(coarse_o, coarse_o, [3, 3, 3, 3], [ts2, ts2, ts2, 1]), len(coarse_o), len(coarse_o))
+        fine_g, fine_o, ts = coarse_g, coarse_o, ts2
+
+
+def test_spconv_maps(cuda):
+    pts = synth.make_sequence(seed=6, n_scans=1, n_elev=64, n_azim=1000)
+    _, coords, _, _ = sp.point_to_voxel(pts[:, :4], [0.1] * 3, [-60, -50, -3, 60, 50, 1], 5, 100000)
+    ind = np.concatenate([np.zeros((len(coords), 1), np.int32), coords], axis=1)
+    gin, _ = ops.unique_coords(torch.from_numpy(ind).to(cuda))
+    rb = ops.build_rulebook(gin, gin, ops.spec_sp_subm([3, 3, 3]))
+    _check(rb, sp.subm_maps(ind, [3, 3, 3]), len(ind), len(ind))
+    shape = [41, 1000, 1200]
+    cur_g, cur_o = gin, ind
+    for ks, st, pd in (([3, 3, 3], [2, 2, 2], [1, 1, 1]), ([3, 3, 3], [2, 2, 2], [1, 1, 1]), ([3, 1, 1], [2, 1, 1], [0, 0, 0])):
+        oind, maps, oshape = sp.sparse_conv_indices(cur_o, shape, ks, st, pd)
+        og = ops.spconv_out_coords(cur_g, ks, st, pd, oshape)
+        rb = ops.build_rulebook(og, cur_g, ops.spec_sp_conv(ks, st, pd))
+        _check(rb, maps, len(cur_o), len(oind))
+        rbi = ops.build_rulebook(cur_g, og, ops.spec_sp_inverse(ks, st, pd))
+        _check(rbi, me.transpose_map(maps), len(oind), len(cur_o))
+        cur_g, cur_o, shape = og, oind, oshape
