@@ -94,7 +94,43 @@ def check(rc, what):
         raise RuntimeError("insmos_b200: %s failed with %s%s" % (what, ERRORS.get(rc, rc), detail))
 
 
+# kernels launched per C-ABI call (memsets not counted) -- used for bench.py's gpu_launches claim
+KERNELS_PER_CALL = {
+    "insmos_table_clear": 1, "insmos_voxelize4d": 5, "insmos_unique_coords": 5, "insmos_spconv_out_coords": 4,
+    "insmos_voxelize3d": 8, "insmos_rulebook_build": 1, "insmos_sparse_conv_fwd": 1, "insmos_linear_fwd": 1,
+    "insmos_affine_act": 1, "insmos_concat2": 1, "insmos_pairsum_add": 1, "insmos_gather_rows": 1,
+    "insmos_segment_mean": 2, "insmos_build_current_points": 1, "insmos_dense_scatter": 1, "insmos_center_decode": 1,
+    "insmos_nms_rotated": 2, "insmos_boxes_to_voxel_units": 1, "insmos_box_membership": 3,
+}
+PROFILE = None        # list collecting (name, start_event, end_event, meta) when profiling is on
+NEXT_META = None      # ops sets this right before a call to attach algorithmic bytes / flops
+
+
+def profile_start():
+    global PROFILE
+    PROFILE = []
+
+
+def profile_stop():
+    """-> list of (name, milliseconds, meta); synchronises."""
+    global PROFILE
+    import torch
+    torch.cuda.synchronize()
+    out = [(n, s.elapsed_time(e), m) for n, s, e, m in PROFILE]
+    PROFILE = None
+    return out
+
+
 def call(name, *args):
-    global LAUNCHES
-    LAUNCHES += 1
+    global LAUNCHES, NEXT_META
+    LAUNCHES += KERNELS_PER_CALL.get(name, 1)
+    if PROFILE is None:
+        check(getattr(load(), name)(*args), name)
+        return
+    import torch
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    meta, NEXT_META = NEXT_META, None
+    s.record()
     check(getattr(load(), name)(*args), name)
+    e.record()
+    PROFILE.append((name, s, e, meta))

@@ -249,9 +249,16 @@ def build_rulebook(out_set, in_set, spec, TM=None):
     pc = torch.zeros(1, dtype=torch.int64, device=dev)
     if in_set.n > (1 << _lib.ROW_BITS):
         raise RuntimeError("insmos_b200.build_rulebook: more than 2^25 input rows")
+    prof = _lib.PROFILE is not None
+    if prof:
+        _lib.NEXT_META = {"n_out": n_out, "K": K, "ncol": out_set.ncol}
     call("insmos_rulebook_build", _p(out_set.coords), n_out, _p(in_set.table), in_set.cap, C.byref(spec), TM,
          _p(seg), _p(entries), _p(pc), None, _stream())
-    return Rulebook(seg, entries, TM, K, n_out, in_set.n, pc)
+    rb = Rulebook(seg, entries, TM, K, n_out, in_set.n, pc)
+    if prof:                               # bytes_alg = coordinate rows read + 8 B per pair written
+        _lib.PROFILE[-1][3]["bytes"] = 4 * out_set.ncol * n_out + 8 * rb.num_pairs
+        _lib.PROFILE[-1][3]["pairs"] = rb.num_pairs
+    return rb
 
 
 # ---- feature ops --------------------------------------------------------------------------------
@@ -280,6 +287,10 @@ def sparse_conv(feat, weight, rb, scale=None, shift=None, bias=None, residual=No
                          % (tuple(feat.shape), tuple(weight.shape), rb.K, rb.n_in))
     out = torch.empty((rb.n_out, Cout), dtype=F32, device=feat.device)
     ep, keep = _epilogue(scale, shift, bias, residual, relu)
+    if _lib.PROFILE is not None:          # algorithmic bytes / flops of this launch (SURVEY 8d formula)
+        P = rb.num_pairs
+        _lib.NEXT_META = {"bytes": 4 * (rb.n_in * Cin + rb.n_out * Cout) + 8 * P + 4 * K * Cin * Cout,
+                          "flops": 2 * P * Cin * Cout, "pairs": P, "K": K, "Cin": Cin, "Cout": Cout, "n_out": rb.n_out}
     call("insmos_sparse_conv_fwd", _p(feat), rb.n_in, Cin, _p(weight), K, Cout, _p(rb.seg), _p(rb.entries), rb.TM,
          _p(out), rb.n_out, C.byref(ep), int(algo), _stream())
     return out

@@ -25,7 +25,7 @@ REF = "/root/reference"
 sys.path[:0] = [os.path.join(ROOT, "oracle", "shims"), REF, ROOT, os.path.join(ROOT, "tests")]
 
 from oracle import build, native  # noqa: E402
-import synth_weights  # noqa: E402
+from insmos_b200 import synth_weights  # noqa: E402
 from insmos_b200 import synth  # noqa: E402
 
 CASES = {
