@@ -109,23 +109,18 @@ def step(net, pts):
 
 def gather_logits(logits, world):
     """the one exchange step of the path: per-point MOS logits of every rank's sample to all ranks (padded)."""
-    import torch.distributed as dist
-    n = torch.tensor([logits.shape[0]], device=logits.device, dtype=torch.int64)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n)
-    mx = int(max(int(s.item()) for s in sizes))
-    pad = torch.zeros((mx, logits.shape[1]), device=logits.device, dtype=logits.dtype)
-    pad[:logits.shape[0]] = logits
-    out = torch.empty((world * mx, logits.shape[1]), device=logits.device, dtype=logits.dtype)
-    dist.all_gather_into_tensor(out, pad)
-    return out, sizes
+    from insmos_b200.distributed import gather_logits as g
+    parts = g(logits, world)
+    return torch.cat(parts, 0), [p.shape[0] for p in parts]
 
 
 def cpu_port_scans_per_sec(sd_cpu, budget_s, steps=1, warmup=0):
     """time oracle/graph.py (CPU port) on a bounded sample: every n-th azimuth of the same scene; result scaled to
     full-size scans/s by the point ratio (cost is linear in points to first order)."""
     from oracle import graph
-    torch.set_num_threads(os.cpu_count() or 1)
+    # the port's hot loops are small MKL GEMMs + index_add; beyond ~16 threads they get slower (measured on the
+    # 128-core GPU host: 128 threads -> 30x slower than 16), so "all the threads it can use" is capped at 16
+    torch.set_num_threads(min(os.cpu_count() or 1, 16))
     frac = min(max((budget_s / max(steps + warmup, 1) - 3.0) / 130.0, 1.0 / 64), 1.0 / 4)
     n_azim = max(int(round(N_AZIM * frac)), 24)
     pts = make_clouds(0, 1, n_azim=n_azim)[0]
@@ -137,7 +132,7 @@ def cpu_port_scans_per_sec(sd_cpu, budget_s, steps=1, warmup=0):
         graph.forward(sd_cpu, pts, timing)
     dt = (time.perf_counter() - t0) / steps
     ratio = n_azim / N_AZIM
-    return {"value": ratio / dt, "unit": "scans/s", "cores": os.cpu_count(), "torch_threads": torch.get_num_threads(),
+    return {"value": ratio / dt, "unit": "scans/s", "cores": torch.get_num_threads(), "host_cores": os.cpu_count(),
             "kind": "port",
             "sample": "%d scans x %d x %d rays (%.1f%% of the C2 points), %.2f s per sample step, scaled to full-size "
                       "scans/s by the point ratio; BLAS = torch MKL; %s" % (N_SCANS, N_ELEV, n_azim, 100 * ratio, dt, CPU_FULL_SCAN_NOTE),

@@ -164,12 +164,23 @@ int insmos_rulebook_build(const int32_t* out_coords, int64_t n_out,
 
 /* sparse convolution forward over a tiled rule book (a3, a8, a12).
  * in [n_in,Cin] f32, weight [K,Cin,Cout] f32, out [n_out,Cout] f32.
- * algo: 0 = auto, 1 = SIMT fp32, 2 = tensor-core 3xTF32 (mma.sync m16n8k8, fp32 accumulate). */
+ * This entry point is the SIMT fp32 FFMA path (any Cin/Cout); `algo` is reserved (pass 0 or 1). */
 int insmos_sparse_conv_fwd(const float* in, int64_t n_in, int32_t Cin,
                            const float* weight, int32_t K, int32_t Cout,
                            const uint16_t* seg, const uint32_t* entries, int32_t TM,
                            float* out, int64_t n_out,
                            const insmos_epilogue_t* ep, int32_t algo, void* stream);
+
+/* Tensor-core path of the same convolution (3xTF32 on mma.sync m16n8k8, fp32 accumulate, fp32-accurate).
+ * The weights are first rearranged ONCE per layer into tensor-core fragment order, pre-split into TF32 hi/lo
+ * (wfrag: insmos_conv_wfrag_elems(K,Cin,Cout) 32-bit words, 16-byte aligned); the convolution then takes wfrag. */
+int64_t insmos_conv_wfrag_elems(int32_t K, int32_t Cin, int32_t Cout);
+int insmos_conv_prep_weights(const float* weight, int32_t K, int32_t Cin, int32_t Cout, void* wfrag, void* stream);
+int insmos_sparse_conv_fwd_tc(const float* in, int64_t n_in, int32_t Cin,
+                              const void* wfrag, int32_t K, int32_t Cout,
+                              const uint16_t* seg, const uint32_t* entries, int32_t TM,
+                              float* out, int64_t n_out,
+                              const insmos_epilogue_t* ep, void* stream);
 
 /* out[n,Cout] = in[n,Cin] . weight[Cin,Cout] + epilogue (ME kernel_size==1 conv, nn.Linear) */
 int insmos_linear_fwd(const float* in, int64_t n, int32_t Cin, const float* weight, int32_t Cout,

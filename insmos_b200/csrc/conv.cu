@@ -66,7 +66,16 @@ k_spconv_simt(const float* __restrict__ in, const float* __restrict__ W,
 }
 
 // ------------------------------------------------------------------------------------------------
-// algo 2: tensor cores, 3xTF32
+// algo 2: tensor cores, 3xTF32, one warp per (tile, group of NT n-tiles)
+//
+// Weights are prepared once per layer (insmos_conv_prep_weights) into tensor-core FRAGMENT ORDER, already split
+// into TF32 hi/lo:  wfrag[k][nt][ks][lane] = uint4{hi(b0), hi(b1), lo(b0), lo(b1)} with, for lane = 4g+t,
+//   b0 = W[k][8ks+2t][8nt+g],  b1 = W[k][8ks+2t+1][8nt+g]   (zero beyond Cin / Cout)
+// so the B operand of one mma is a single coalesced 16-byte load (L1/L2 resident), no conversions in the loop.
+// The contraction index is permuted (k-slots t, t+4 <-> channels 2t, 2t+1) so that the A operand of a gathered
+// row is one 8-byte load per 8 channels.  Every warp is independent (own tile rows x own channel columns of the
+// shared-memory accumulator): no block barriers; thousands of warps per layer hide the gather latency, and the
+// next chunk's rule-book entries are prefetched while the current chunk is multiplied.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
     const float r = x - __uint_as_float(hi);
@@ -78,120 +87,187 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__global__ void k_prep_weights(const float* __restrict__ W, int K, int Cin, int Cout, int KS, int NT8, uint4* __restrict__ wf) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)K * NT8 * KS * 32;
+    if (idx >= total) return;
+    const int lane = (int)(idx & 31);
+    int64_t r = idx >> 5;
+    const int ks = (int)(r % KS); r /= KS;
+    const int nt = (int)(r % NT8);
+    const int k = (int)(r / NT8);
+    const int g = lane >> 2, t = lane & 3;
+    const int c0 = ks * 8 + 2 * t, n = nt * 8 + g;
+    float b0 = 0.f, b1 = 0.f;
+    if (n < Cout) {
+        if (c0 < Cin) b0 = W[((int64_t)k * Cin + c0) * Cout + n];
+        if (c0 + 1 < Cin) b1 = W[((int64_t)k * Cin + c0 + 1) * Cout + n];
+    }
+    uint4 v;
+    split_tf32(b0, v.x, v.z);
+    split_tf32(b1, v.y, v.w);
+    wf[idx] = v;
+}
+
+extern "C" int64_t insmos_conv_wfrag_elems(int32_t K, int32_t Cin, int32_t Cout) {
+    return (int64_t)K * ((Cout + 7) / 8) * ((Cin + 7) / 8) * 32 * 4;      // number of 32-bit words
+}
+extern "C" int insmos_conv_prep_weights(const float* weight, int32_t K, int32_t Cin, int32_t Cout, void* wfrag, void* stream) {
+    if (!weight || !wfrag || K <= 0 || Cin <= 0 || Cout <= 0) return INSMOS_ERR_INVALID_ARG;
+    const int KS = (Cin + 7) / 8, NT8 = (Cout + 7) / 8;
+    const int64_t total = (int64_t)K * NT8 * KS * 32;
+    k_prep_weights<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(weight, K, Cin, Cout, KS, NT8, (uint4*)wfrag);
+    INSMOS_CHECK_LAUNCH("k_prep_weights");
+    return INSMOS_OK;
+}
+
 #define MMA_WARPS 4
-// NT: n-tiles (8 output channels each) per warp; WN: warps sharing one tile along Cout.
-// A block of 4 warps processes 4/WN tiles; warps never synchronise with each other (each owns
-// disjoint accumulator columns).
-// Fragment mapping (g = lane>>2, t = lane&3): the contraction index is permuted so that one lane's
-// two k-slots (t, t+4) are the adjacent channels (2t, 2t+1) -> one 8-byte load per gathered row.
-template <int NT, int WN>
+template <int NT>
 __global__ void __launch_bounds__(MMA_WARPS * 32)
-k_spconv_mma(const float* __restrict__ in, const float* __restrict__ W,
-             const uint16_t* __restrict__ seg, const uint32_t* __restrict__ entries,
-             float* __restrict__ out, int64_t n_out, int64_t n_tiles, int Cin, int Cout, int K, int TM,
-             insmos_epilogue_t ep) {
-    constexpr int TPB = MMA_WARPS / WN;
-    constexpr int CP = WN * NT * 8;                    // padded Cout held in shared memory
-    extern __shared__ float sm[];
+k_spconv_tc(const float* __restrict__ in, const uint4* __restrict__ wf,
+            const uint16_t* __restrict__ seg, const uint32_t* __restrict__ entries,
+            float* __restrict__ out, int64_t n_out, int64_t n_tiles, int groups, int Cin, int Cout, int K, int TM,
+            int KS, int NT8, insmos_epilogue_t ep) {
+    constexpr int CW = NT * 8;                               // channel columns owned by this warp
+    extern __shared__ __align__(16) float sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int tib = warp / WN, wn = warp % WN;
-    const int64_t tile = (int64_t)blockIdx.x * TPB + tib;
-    if (tile >= n_tiles) return;                       // warps are independent: no block barrier below
-    float* acc = sm + (size_t)tib * TM * CP;           // [TM][CP]
-    int* sseg = reinterpret_cast<int*>(sm + (size_t)TPB * TM * CP) + warp * (K + 1);
+    const int64_t wglobal = (int64_t)blockIdx.x * MMA_WARPS + warp;
+    const int64_t tile = wglobal / groups;
+    const int grp = (int)(wglobal - tile * groups);
+    if (tile >= n_tiles) return;                             // warps are independent: no block barrier below
+    float* acc = sm + (size_t)warp * TM * CW;                // [TM][CW]
+    int* sseg = reinterpret_cast<int*>(sm + (size_t)MMA_WARPS * TM * CW) + warp * (K + 1);
     const uint16_t* tseg = seg + tile * (K + 1);
     for (int k = lane; k <= K; k += 32) sseg[k] = tseg[k];
-    const int cbase = wn * NT * 8;
-    for (int i = lane; i < TM * NT * 8; i += 32) acc[(i / (NT * 8)) * CP + cbase + (i % (NT * 8))] = 0.0f;
+    for (int i = lane; i < TM * CW; i += 32) acc[i] = 0.0f;
     __syncwarp();
     const uint32_t* tent = entries + tile * (int64_t)TM * K;
-    const int KS = (Cin + 7) >> 3;
     const bool even = (Cin & 1) == 0;
-    for (int k = 0; k < K; ++k) {
-        const int s0 = sseg[k], n = sseg[k + 1] - s0;
-        if (n == 0) continue;
-        const float* Wk = W + (int64_t)k * Cin * Cout;
-        for (int c0 = 0; c0 < n; c0 += 16) {
-            const bool v_lo = (c0 + g) < n, v_hi = (c0 + g + 8) < n;
-            const uint32_t e_lo = v_lo ? __ldg(tent + s0 + c0 + g) : 0u;
-            const uint32_t e_hi = v_hi ? __ldg(tent + s0 + c0 + g + 8) : 0u;
-            const float* x_lo = in + (int64_t)(e_lo & INSMOS_ROW_MASK) * Cin;
-            const float* x_hi = in + (int64_t)(e_hi & INSMOS_ROW_MASK) * Cin;
-            float d[NT][4];
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) { d[nt][0] = d[nt][1] = d[nt][2] = d[nt][3] = 0.0f; }
-            for (int ks = 0; ks < KS; ++ks) {
-                const int col = ks * 8 + 2 * t;
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;     // (g,2t) (g+8,2t) (g,2t+1) (g+8,2t+1)
-                if (even) {
-                    if (col < Cin) {
-                        if (v_lo) { const float2 v = __ldg(reinterpret_cast<const float2*>(x_lo + col)); a0 = v.x; a2 = v.y; }
-                        if (v_hi) { const float2 v = __ldg(reinterpret_cast<const float2*>(x_hi + col)); a1 = v.x; a3 = v.y; }
-                    }
-                } else {
-                    if (col < Cin) { if (v_lo) a0 = __ldg(x_lo + col); if (v_hi) a1 = __ldg(x_hi + col); }
-                    if (col + 1 < Cin) { if (v_lo) a2 = __ldg(x_lo + col + 1); if (v_hi) a3 = __ldg(x_hi + col + 1); }
-                }
-                uint32_t ah[4], al[4];
-                split_tf32(a0, ah[0], al[0]); split_tf32(a1, ah[1], al[1]);
-                split_tf32(a2, ah[2], al[2]); split_tf32(a3, ah[3], al[3]);
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    const int nc = cbase + nt * 8 + g;
-                    float b0 = 0.f, b1 = 0.f;
-                    if (nc < Cout) {
-                        if (col < Cin) b0 = __ldg(Wk + col * Cout + nc);
-                        if (col + 1 < Cin) b1 = __ldg(Wk + (col + 1) * Cout + nc);
-                    }
-                    uint32_t bh0, bl0, bh1, bl1;
-                    split_tf32(b0, bh0, bl0); split_tf32(b1, bh1, bl1);
-                    mma_tf32(d[nt], al, bh0, bh1);
-                    mma_tf32(d[nt], ah, bl0, bl1);
-                    mma_tf32(d[nt], ah, bh0, bh1);
-                }
-            }
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                const int cc = cbase + nt * 8 + 2 * t;
-                if (v_lo) {
-                    float2* p = reinterpret_cast<float2*>(acc + (e_lo >> INSMOS_ROW_BITS) * CP + cc);
-                    float2 v = *p; v.x += d[nt][0]; v.y += d[nt][1]; *p = v;
-                }
-                if (v_hi) {
-                    float2* p = reinterpret_cast<float2*>(acc + (e_hi >> INSMOS_ROW_BITS) * CP + cc);
-                    float2 v = *p; v.x += d[nt][2]; v.y += d[nt][3]; *p = v;
-                }
-            }
-            __syncwarp();
+    const int nt0 = grp * NT;
+
+    // chunk iterator over the non-empty buckets: (k, s0, n, c0)
+    int k = -1, s0 = 0, n = 0, c0 = 0;
+    auto advance = [&]() -> bool {
+        c0 += 16;
+        while (c0 >= n) {
+            if (++k >= K) return false;
+            s0 = sseg[k]; n = sseg[k + 1] - s0; c0 = 0;
         }
+        return true;
+    };
+    bool have = advance();
+    bool v_lo = false, v_hi = false;
+    uint32_t e_lo = 0u, e_hi = 0u;
+    if (have) {
+        v_lo = (c0 + g) < n; v_hi = (c0 + g + 8) < n;
+        if (v_lo) e_lo = __ldg(tent + s0 + c0 + g);
+        if (v_hi) e_hi = __ldg(tent + s0 + c0 + g + 8);
+    }
+    while (have) {
+        const int kc = k;
+        const bool cv_lo = v_lo, cv_hi = v_hi;
+        const uint32_t ce_lo = e_lo, ce_hi = e_hi;
+        have = advance();                                    // prefetch the next chunk's entries
+        if (have) {
+            v_lo = (c0 + g) < n; v_hi = (c0 + g + 8) < n;
+            e_lo = v_lo ? __ldg(tent + s0 + c0 + g) : 0u;
+            e_hi = v_hi ? __ldg(tent + s0 + c0 + g + 8) : 0u;
+        }
+        const float* x_lo = in + (int64_t)(ce_lo & INSMOS_ROW_MASK) * Cin;
+        const float* x_hi = in + (int64_t)(ce_hi & INSMOS_ROW_MASK) * Cin;
+        const uint4* wk = wf + ((int64_t)kc * NT8 + nt0) * KS * 32 + lane;
+        float d[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) { d[j][0] = d[j][1] = d[j][2] = d[j][3] = 0.0f; }
+#pragma unroll 2
+        for (int ks = 0; ks < KS; ++ks) {
+            const int col = ks * 8 + 2 * t;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // (g,2t) (g+8,2t) (g,2t+1) (g+8,2t+1)
+            if (even) {
+                if (col < Cin) {
+                    if (cv_lo) { const float2 v = __ldg(reinterpret_cast<const float2*>(x_lo + col)); a0 = v.x; a2 = v.y; }
+                    if (cv_hi) { const float2 v = __ldg(reinterpret_cast<const float2*>(x_hi + col)); a1 = v.x; a3 = v.y; }
+                }
+            } else {
+                if (col < Cin) { if (cv_lo) a0 = __ldg(x_lo + col); if (cv_hi) a1 = __ldg(x_hi + col); }
+                if (col + 1 < Cin) { if (cv_lo) a2 = __ldg(x_lo + col + 1); if (cv_hi) a3 = __ldg(x_hi + col + 1); }
+            }
+            uint4 b[NT];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) b[j] = __ldg(wk + ((int64_t)j * KS + ks) * 32);
+            uint32_t ah[4], al[4];
+            split_tf32(a0, ah[0], al[0]); split_tf32(a1, ah[1], al[1]);
+            split_tf32(a2, ah[2], al[2]); split_tf32(a3, ah[3], al[3]);
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                mma_tf32(d[j], al, b[j].x, b[j].y);
+                mma_tf32(d[j], ah, b[j].z, b[j].w);
+                mma_tf32(d[j], ah, b[j].x, b[j].y);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int cc = j * 8 + 2 * t;
+            if (cv_lo) {
+                float2* p = reinterpret_cast<float2*>(acc + (ce_lo >> INSMOS_ROW_BITS) * CW + cc);
+                float2 v = *p; v.x += d[j][0]; v.y += d[j][1]; *p = v;
+            }
+            if (cv_hi) {
+                float2* p = reinterpret_cast<float2*>(acc + (ce_hi >> INSMOS_ROW_BITS) * CW + cc);
+                float2 v = *p; v.x += d[j][2]; v.y += d[j][3]; *p = v;
+            }
+        }
+        __syncwarp();
     }
     const int64_t row0 = tile * TM;
     const int rows = (int)((n_out - row0) < TM ? (n_out - row0) : TM);
-    constexpr int CW = NT * 8;
+    const int cbase = nt0 * 8;
     for (int i = lane; i < rows * CW; i += 32) {
         const int r = i / CW, c = cbase + (i % CW);
-        if (c < Cout) out[(row0 + r) * Cout + c] = apply_epilogue(acc[r * CP + c], c, row0 + r, Cout, ep);
+        if (c < Cout) out[(row0 + r) * Cout + c] = apply_epilogue(acc[i], c, row0 + r, Cout, ep);
     }
 }
 
-template <int NT, int WN>
-static int launch_mma(const float* in, const float* W, const uint16_t* seg, const uint32_t* entries, float* out,
-                      int64_t n_out, int Cin, int Cout, int K, int TM, const insmos_epilogue_t& ep, cudaStream_t st) {
-    constexpr int TPB = MMA_WARPS / WN;
-    constexpr int CP = WN * NT * 8;
-    const size_t smem = sizeof(float) * (size_t)TPB * TM * CP + sizeof(int) * (size_t)MMA_WARPS * (K + 1);
+template <int NT>
+static int launch_tc(const float* in, const void* wf, const uint16_t* seg, const uint32_t* entries, float* out,
+                     int64_t n_out, int Cin, int Cout, int K, int TM, const insmos_epilogue_t& ep, cudaStream_t st) {
+    const int KS = (Cin + 7) / 8, NT8 = (Cout + 7) / 8;
+    const int groups = (NT8 + NT - 1) / NT;
+    const size_t smem = sizeof(float) * (size_t)MMA_WARPS * TM * NT * 8 + sizeof(int) * (size_t)MMA_WARPS * (K + 1);
     if (smem > 220 * 1024) return INSMOS_ERR_UNSUPPORTED;
     static thread_local size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_spconv_mma<NT, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_spconv_tc<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     const int64_t n_tiles = ceil_div64(n_out, TM);
-    k_spconv_mma<NT, WN><<<(unsigned)ceil_div64(n_tiles, TPB), MMA_WARPS * 32, smem, st>>>(
-        in, W, seg, entries, out, n_out, n_tiles, Cin, Cout, K, TM, ep);
-    INSMOS_CHECK_LAUNCH("k_spconv_mma");
+    const int64_t warps = n_tiles * groups;
+    k_spconv_tc<NT><<<(unsigned)ceil_div64(warps, MMA_WARPS), MMA_WARPS * 32, smem, st>>>(
+        in, (const uint4*)wf, seg, entries, out, n_out, n_tiles, groups, Cin, Cout, K, TM, KS, NT8, ep);
+    INSMOS_CHECK_LAUNCH("k_spconv_tc");
     return INSMOS_OK;
+}
+
+extern "C" int insmos_sparse_conv_fwd_tc(const float* in, int64_t n_in, int32_t Cin,
+                                         const void* wfrag, int32_t K, int32_t Cout,
+                                         const uint16_t* seg, const uint32_t* entries, int32_t TM,
+                                         float* out, int64_t n_out,
+                                         const insmos_epilogue_t* ep_in, void* stream) {
+    if ((n_in > 0 && !in) || !wfrag || !seg || !entries || (n_out > 0 && !out) || Cin <= 0 || Cout <= 0 || K <= 0 || n_out < 0 || n_in < 0)
+        return INSMOS_ERR_INVALID_ARG;
+    if (TM != 16 && TM != 32 && TM != 64 && TM != 128) return INSMOS_ERR_INVALID_ARG;
+    if (n_in > (int64_t)INSMOS_ROW_MASK + 1) return INSMOS_ERR_UNSUPPORTED;
+    insmos_epilogue_t ep = {nullptr, nullptr, nullptr, nullptr, 0};
+    if (ep_in) ep = *ep_in;
+    if (ep.scale && !ep.shift) return INSMOS_ERR_INVALID_ARG;
+    if (n_out == 0) return INSMOS_OK;
+    const int NT8 = (Cout + 7) / 8;
+    const int64_t n_tiles = ceil_div64(n_out, TM);
+    // two n-tiles per warp halve the redundant A gathers; only when that still leaves thousands of warps
+    if (NT8 % 2 == 0 && n_tiles * (NT8 / 2) >= 4096)
+        return launch_tc<2>(in, wfrag, seg, entries, out, n_out, Cin, Cout, K, TM, ep, (cudaStream_t)stream);
+    return launch_tc<1>(in, wfrag, seg, entries, out, n_out, Cin, Cout, K, TM, ep, (cudaStream_t)stream);
 }
 
 extern "C" int insmos_sparse_conv_fwd(const float* in, int64_t n_in, int32_t Cin,
@@ -199,6 +275,7 @@ extern "C" int insmos_sparse_conv_fwd(const float* in, int64_t n_in, int32_t Cin
                                       const uint16_t* seg, const uint32_t* entries, int32_t TM,
                                       float* out, int64_t n_out,
                                       const insmos_epilogue_t* ep_in, int32_t algo, void* stream) {
+    (void)algo;                                              // SIMT fp32 reference path (see insmos_sparse_conv_fwd_tc)
     if ((n_in > 0 && !in) || !weight || !seg || !entries || (n_out > 0 && !out) || Cin <= 0 || Cout <= 0 || K <= 0 || n_out < 0 || n_in < 0)
         return INSMOS_ERR_INVALID_ARG;
     if (TM != 16 && TM != 32 && TM != 64 && TM != 128) return INSMOS_ERR_INVALID_ARG;
@@ -208,17 +285,6 @@ extern "C" int insmos_sparse_conv_fwd(const float* in, int64_t n_in, int32_t Cin
     if (ep.scale && !ep.shift) return INSMOS_ERR_INVALID_ARG;
     if (n_out == 0) return INSMOS_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (algo == 0) algo = (Cin >= 8 && Cout <= 128) ? 2 : 1;
-    if (algo == 2) {
-        const int nt8 = (Cout + 7) / 8;
-        if (nt8 <= 1) return launch_mma<1, 1>(in, weight, seg, entries, out, n_out, Cin, Cout, K, TM, ep, st);
-        if (nt8 <= 2) return launch_mma<2, 1>(in, weight, seg, entries, out, n_out, Cin, Cout, K, TM, ep, st);
-        if (nt8 <= 4) return launch_mma<2, 2>(in, weight, seg, entries, out, n_out, Cin, Cout, K, TM, ep, st);
-        if (nt8 <= 8) return launch_mma<2, 4>(in, weight, seg, entries, out, n_out, Cin, Cout, K, TM, ep, st);
-        if (nt8 <= 16) return launch_mma<4, 4>(in, weight, seg, entries, out, n_out, Cin, Cout, K, TM, ep, st);
-        return INSMOS_ERR_UNSUPPORTED;
-    }
-    if (algo != 1) return INSMOS_ERR_INVALID_ARG;
     const size_t smem = sizeof(float) * (size_t)TM * Cout + sizeof(int) * (size_t)(K + 1);
     if (smem > 220 * 1024) return INSMOS_ERR_UNSUPPORTED;
     static thread_local size_t configured = 0;

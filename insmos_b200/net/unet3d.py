@@ -152,9 +152,15 @@ class UNetV2(nn.Module):
         batch_dict = self.bev_backbone(batch_dict)
         batch_dict = self.center_head(batch_dict, Model_mode)
         pred_dicts, recall_dicts = post_processing(batch_dict, self.post_process, self.num_class)
+        if batch_dict.get("instance_boxes_override") is not None:
+            # externally supplied detections for the instance-fusion stage (e.g. a tracker's boxes; the parity
+            # tests use it to compare the decoder under identical discrete decisions).  pred_dicts is still returned.
+            fuse_from = batch_dict["instance_boxes_override"]
+        else:
+            fuse_from = pred_dicts[0]
 
         # ---- upsample fusion with per-level instance bits (Array_Index on device)
-        inst = InstanceBoxes(pred_dicts[0], self.point_cloud_range[0:3], self.voxel_size,
+        inst = InstanceBoxes(fuse_from, self.point_cloud_range[0:3], self.voxel_size,
                              batch_dict["encoded_spconv_tensor_stride"], self.num_class)
         inv_bev = self.inv_conv_out(out)
         f, _ = inst.concat_bits(inv_bev.features, inv_bev.indices, 1)

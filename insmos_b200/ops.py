@@ -230,7 +230,8 @@ class Rulebook:
 
 
 def choose_tile_rows(n_out, K):
-    tm = 128 if n_out >= 300_000 else 64 if n_out >= 100_000 else 32 if n_out >= 20_000 else 16
+    # enough tiles that every layer exposes thousands of independent warps (one warp per tile x channel group)
+    tm = 128 if n_out >= 300_000 else 64 if n_out >= 150_000 else 32 if n_out >= 75_000 else 16
     while tm > 16 and tm * K >= 65536:
         tm //= 2
     return tm
@@ -276,9 +277,28 @@ def _epilogue(scale=None, shift=None, bias=None, residual=None, relu=False):
     return ep, keep
 
 
+_WFRAG_CACHE = {}
+
+
+def prepared_weights(weight):
+    """tensor-core fragment-ordered, TF32 hi/lo pre-split copy of a [K,Cin,Cout] weight (insmos_conv_prep_weights),
+    cached until the tensor is modified in place or freed (layers are constant at inference)."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device.index)
+    hit = _WFRAG_CACHE.get(key)
+    if hit is not None:
+        return hit[0]
+    K, Cin, Cout = weight.shape
+    wf = torch.empty(_lib.load().insmos_conv_wfrag_elems(K, Cin, Cout), dtype=I32, device=weight.device)
+    call("insmos_conv_prep_weights", _p(weight), K, Cin, Cout, _p(wf), _stream())
+    if len(_WFRAG_CACHE) > 512:
+        _WFRAG_CACHE.clear()
+    _WFRAG_CACHE[key] = (wf, weight)            # keep the source alive so the data_ptr cannot be recycled
+    return wf
+
+
 def sparse_conv(feat, weight, rb, scale=None, shift=None, bias=None, residual=None, relu=False, algo=0):
     """out[n_out,Cout] = sum over rule-book pairs of feat[in] @ weight[k] (+ fused epilogue).
-    weight [K,Cin,Cout] f32."""
+    weight [K,Cin,Cout] f32.  algo: 0/2 = tensor cores (3xTF32, fp32-accurate), 1 = SIMT fp32 reference path."""
     feat = _req(feat, F32, "sparse_conv")
     weight = _req(weight, F32, "sparse_conv")
     K, Cin, Cout = weight.shape
@@ -287,12 +307,17 @@ def sparse_conv(feat, weight, rb, scale=None, shift=None, bias=None, residual=No
                          % (tuple(feat.shape), tuple(weight.shape), rb.K, rb.n_in))
     out = torch.empty((rb.n_out, Cout), dtype=F32, device=feat.device)
     ep, keep = _epilogue(scale, shift, bias, residual, relu)
+    wf = prepared_weights(weight) if algo != 1 else None
     if _lib.PROFILE is not None:          # algorithmic bytes / flops of this launch (SURVEY 8d formula)
         P = rb.num_pairs
         _lib.NEXT_META = {"bytes": 4 * (rb.n_in * Cin + rb.n_out * Cout) + 8 * P + 4 * K * Cin * Cout,
                           "flops": 2 * P * Cin * Cout, "pairs": P, "K": K, "Cin": Cin, "Cout": Cout, "n_out": rb.n_out}
-    call("insmos_sparse_conv_fwd", _p(feat), rb.n_in, Cin, _p(weight), K, Cout, _p(rb.seg), _p(rb.entries), rb.TM,
-         _p(out), rb.n_out, C.byref(ep), int(algo), _stream())
+    if algo == 1:
+        call("insmos_sparse_conv_fwd", _p(feat), rb.n_in, Cin, _p(weight), K, Cout, _p(rb.seg), _p(rb.entries), rb.TM,
+             _p(out), rb.n_out, C.byref(ep), 1, _stream())
+    else:
+        call("insmos_sparse_conv_fwd_tc", _p(feat), rb.n_in, Cin, _p(wf), K, Cout, _p(rb.seg), _p(rb.entries), rb.TM,
+             _p(out), rb.n_out, C.byref(ep), _stream())
     return out
 
 

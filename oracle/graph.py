@@ -204,7 +204,7 @@ def post_process(cls_preds, box_preds):
         selected = idx[order[keep][:PP["NMS_POST_MAXSIZE"]]]
     selected = mask.nonzero().view(-1)[selected]
     return {"pred_boxes": boxes[selected], "pred_scores": scores[selected], "pred_labels": labels[selected],
-            "n_cand": int(mask.sum())}
+            "n_cand": int(mask.sum()), "all_scores": scores, "all_boxes": boxes, "all_labels": labels}
 
 
 def instance_bits(ind, boxes8):
@@ -212,7 +212,7 @@ def instance_bits(ind, boxes8):
     return torch.from_numpy(native.find_features_by_bbox_with_yaw(xyz, boxes8.numpy())).float()
 
 
-def unet(sd, voxel_features, voxel_coords, pc_voxel_id, timing=None):
+def unet(sd, voxel_features, voxel_coords, pc_voxel_id, timing=None, pred_override=None):
     """spconv_unet.py:267-416.  voxel_coords [M,4] (0,z,y,x)"""
     p = "model.unet."
     s = _SP(sd, p)
@@ -234,12 +234,13 @@ def unet(sd, voxel_features, voxel_coords, pc_voxel_id, timing=None):
     t2 = time.perf_counter()
     pred = post_process(cls, boxes)
     t3 = time.perf_counter()
+    fuse = pred if pred_override is None else pred_override
 
-    b = pred["pred_boxes"].clone()
+    b = torch.as_tensor(fuse["pred_boxes"]).clone()
     for dd in range(3):                                                   # spconv_unet.py:324-329
         b[:, dd] = (b[:, dd] - PC_RANGE[dd]) / VOXEL[dd] / 8
         b[:, 3 + dd] = b[:, 3 + dd] / VOXEL[dd] / 8
-    b8 = torch.hstack([b, pred["pred_labels"].view(-1, 1)])
+    b8 = torch.hstack([b, torch.as_tensor(fuse["pred_labels"]).view(-1, 1).to(b.dtype)])
 
     def with_bits(t):
         bits = instance_bits(t[1], b8)
@@ -276,7 +277,7 @@ def unet(sd, voxel_features, voxel_coords, pc_voxel_id, timing=None):
     return logits, pred
 
 
-def forward(sd, points, timing=None):
+def forward(sd, points, timing=None, pred_override=None):
     """models.py:297-376 ('test' mode, one sample).  Returns dict with logits [Nc,3] and detections."""
     sd = {k: torch.as_tensor(v) for k, v in sd.items()}
     t0 = time.perf_counter()
@@ -286,7 +287,7 @@ def forward(sd, points, timing=None):
     vf = sp.mean_vfe(vox, num)
     vc = np.concatenate([np.zeros((len(coords), 1), np.int32), coords], axis=1)
     t2 = time.perf_counter()
-    logits, pred = unet(sd, vf, vc, ids, timing)
+    logits, pred = unet(sd, vf, vc, ids, timing, pred_override)
     if timing is not None:
         timing.update({"motionnet_s": t1 - t0, "voxelize3d_s": t2 - t1, "total_s": time.perf_counter() - t0})
     return {"logits": logits, "current_point": cur, "voxel_coords": vc, "voxel_features": vf, "pc_voxel_id": ids, **pred}

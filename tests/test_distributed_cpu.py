@@ -1,0 +1,40 @@
+"""N>1 host logic on CPU: world_size-2 gloo, sample sharding + the single padded gather of logits."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from insmos_b200 import distributed as D
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mine = D.shard_samples(5, rank, world)
+        g = torch.Generator().manual_seed(rank)
+        logits = torch.randn((1000 + 137 * rank, 3), generator=g)
+        parts = D.gather_logits(logits, world)
+        ok = len(parts) == world
+        for r in range(world):
+            exp = torch.randn((1000 + 137 * r, 3), generator=torch.Generator().manual_seed(r))
+            ok = ok and torch.equal(parts[r], exp)
+        ret[rank] = (ok, mine)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_and_gather_world2():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, 29611, ret), nprocs=world, join=True)
+    assert ret[0][0] and ret[1][0]
+    assert ret[0][1] == [0, 2, 4] and ret[1][1] == [1, 3]
+
+
+def test_single_rank_is_identity():
+    x = torch.randn(10, 3)
+    assert D.gather_logits(x, 1)[0] is x
+    assert D.shard_samples(8, 3, 8) == [3]
