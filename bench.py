@@ -247,6 +247,9 @@ def main():
         if meta:
             f["bytes"] += meta.get("bytes", 0) / 2
             f["flops"] += meta.get("flops", 0) / 2
+    conv_launches = sorted(({"ms": round(t, 4), **{k: m[k] for k in ("K", "Cin", "Cout", "n_out", "pairs")},
+                             "alg_GBps": round(m["bytes"] / (t * 1e-3) / 1e9, 1)}
+                            for name, t, m in prof[len(prof) // 2:] if m and "Cin" in m), key=lambda d: -d["ms"])[:16]
     peak, peak_src = peaks()
     top = max((k for k in fam if fam[k]["bytes"] > 0), key=lambda k: fam[k]["ms"])
     ach = fam[top]["bytes"] / (fam[top]["ms"] * 1e-3) / 1e9
@@ -283,7 +286,7 @@ def main():
             "e2e": {"value": round(e2e_value, 3), "unit": "scans/s", "ms_per_step": round(ms_e2e / args.steps, 4),
                     "h2d_bytes_per_step": int(host[0].numel() * 4), "d2h_bytes_per_step": int(n_cur * 3 * 4)},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
-            "kernels": kernels, "profiled_step_ms": round(step_ms_prof, 3),
+            "kernels": kernels, "slowest_sparse_convs": conv_launches, "profiled_step_ms": round(step_ms_prof, 3),
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu

@@ -213,11 +213,26 @@ int insmos_build_current_points(const float* points, int32_t point_stride, const
 int insmos_dense_scatter(const float* feat, const int32_t* coords, int64_t n, int32_t C,
                          int32_t D, int32_t H, int32_t W, float* out, void* stream);
 
+/* Dense BEV convolutions on tensor cores (3xTF32, fp32-accurate), NHWC activations [H*W, C] (a9;
+ * base_bev_backbone.py:84-115).  weight [taps, Cin, Cout] f32 with BatchNorm(eval) pre-folded, bias [Cout] or NULL.
+ * mode 0: 3x3 stride 1 zero-pad 1 (taps=9, tap = ky*3+kx); mode 1: 1x1 (taps=1); mode 2: 2x2 stride-2 transposed
+ * conv (taps=4, tap = dy*2+dx, out is [2H*2W, Cout]).  Requires Cin % 32 == 0 and Cout % 128 == 0. */
+int insmos_conv2d_nhwc_tc(const float* in, int32_t H, int32_t W, int32_t Cin,
+                          const float* weight, int32_t mode, int32_t Cout,
+                          const float* bias, int32_t relu, float* out, void* stream);
+
+/* SparseConvTensor.dense() + HeightCompression view, channels-last: out[(y*W+x), c*D+z] (height_compression.py:26-30) */
+int insmos_dense_scatter_nhwc(const float* feat, const int32_t* coords, int64_t n, int32_t C,
+                              int32_t D, int32_t H, int32_t W, float* out, void* stream);
+
 /* ---- detection head ----------------------------------------------------------------------- */
 
 /* CenterHead decode + sigmoid/max (center_head.py:251-276, post_process.py:146-192).
- * cls [ncls,H,W], box [8,H,W] (NCHW conv outputs, batch 1).  boxes [H*W,7], scores [H*W], labels [H*W] (1-based). */
-int insmos_center_decode(const float* cls, const float* box, int32_t ncls, int32_t H, int32_t W,
+ * cls / box are the head outputs for batch 1 in any layout: element (channel c, pixel i) of cls is
+ * cls[c*cls_cs + i*cls_ps] (NCHW: cs=H*W, ps=1; NHWC [H*W,stride]: cs=1, ps=stride), same for box (8 channels).
+ * boxes [H*W,7], scores [H*W], labels [H*W] (1-based). */
+int insmos_center_decode(const float* cls, int64_t cls_cs, int64_t cls_ps, const float* box, int64_t box_cs, int64_t box_ps,
+                         int32_t ncls, int32_t H, int32_t W,
                          float out_size_factor, float vx, float vy, float x_min, float y_min,
                          float* boxes, float* scores, int32_t* labels, void* stream);
 

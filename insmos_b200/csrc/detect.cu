@@ -12,7 +12,9 @@
 #include <math.h>
 
 // ------------------------------------------------------------------------------------------------
-__global__ void k_center_decode(const float* __restrict__ cls, const float* __restrict__ box, int ncls, int H, int W,
+#define BOXV(c) box[(int64_t)(c) * box_cs + (int64_t)i * box_ps]
+__global__ void k_center_decode(const float* __restrict__ cls, int64_t cls_cs, int64_t cls_ps,
+                                const float* __restrict__ box, int64_t box_cs, int64_t box_ps, int ncls, int H, int W,
                                 float osf, float vx, float vy, float x_min, float y_min,
                                 float* __restrict__ boxes, float* __restrict__ scores, int32_t* __restrict__ labels) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -20,27 +22,29 @@ __global__ void k_center_decode(const float* __restrict__ cls, const float* __re
     if (i >= HW) return;
     const int y = i / W, x = i - y * W;
     // xs = (x + reg0) * OUT_SIZE_FACTOR * VOXEL_SIZE[0] + range_min   (center_head.py:264-268), fp32, left to right
-    float xs = __fadd_rn((float)x, box[0 * HW + i]);
-    float ys = __fadd_rn((float)y, box[1 * HW + i]);
+    float xs = __fadd_rn((float)x, BOXV(0));
+    float ys = __fadd_rn((float)y, BOXV(1));
     xs = __fadd_rn(__fmul_rn(__fmul_rn(xs, osf), vx), x_min);
     ys = __fadd_rn(__fmul_rn(__fmul_rn(ys, osf), vy), y_min);
     float* o = boxes + (int64_t)i * 7;
-    o[0] = xs; o[1] = ys; o[2] = box[2 * HW + i];
-    o[3] = expf(box[3 * HW + i]); o[4] = expf(box[4 * HW + i]); o[5] = expf(box[5 * HW + i]);
-    o[6] = atan2f(box[6 * HW + i], box[7 * HW + i]);
+    o[0] = xs; o[1] = ys; o[2] = BOXV(2);
+    o[3] = expf(BOXV(3)); o[4] = expf(BOXV(4)); o[5] = expf(BOXV(5));
+    o[6] = atan2f(BOXV(6), BOXV(7));
     float best = -1.0f; int bi = 0;
     for (int c = 0; c < ncls; ++c) {
-        const float l = cls[c * HW + i];
+        const float l = cls[(int64_t)c * cls_cs + (int64_t)i * cls_ps];
         const float s = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-l)));      // torch.sigmoid
         if (s > best) { best = s; bi = c; }                              // first maximum wins (torch.max)
     }
     scores[i] = best; labels[i] = bi + 1;
 }
-extern "C" int insmos_center_decode(const float* cls, const float* box, int32_t ncls, int32_t H, int32_t W,
+extern "C" int insmos_center_decode(const float* cls, int64_t cls_cs, int64_t cls_ps, const float* box, int64_t box_cs,
+                                    int64_t box_ps, int32_t ncls, int32_t H, int32_t W,
                                     float out_size_factor, float vx, float vy, float x_min, float y_min,
                                     float* boxes, float* scores, int32_t* labels, void* stream) {
     if (!cls || !box || !boxes || !scores || !labels || ncls <= 0 || H <= 0 || W <= 0) return INSMOS_ERR_INVALID_ARG;
-    k_center_decode<<<(H * W + 255) / 256, 256, 0, (cudaStream_t)stream>>>(cls, box, ncls, H, W, out_size_factor, vx, vy,
+    k_center_decode<<<(H * W + 255) / 256, 256, 0, (cudaStream_t)stream>>>(cls, cls_cs, cls_ps, box, box_cs, box_ps, ncls, H, W,
+                                                                            out_size_factor, vx, vy,
                                                                             x_min, y_min, boxes, scores, labels);
     INSMOS_CHECK_LAUNCH("k_center_decode");
     return INSMOS_OK;
@@ -151,8 +155,19 @@ k_nms_mask(const float* __restrict__ boxes, int n, float thresh, unsigned long l
 #pragma unroll
         for (int k = 0; k < 7; ++k) a[k] = boxes[(int64_t)i * 7 + k];
         const int start = (rb == cb) ? threadIdx.x + 1 : 0;
-        for (int j = start; j < ncol; ++j)
-            if (rot_iou_bev(a, sb + j * 7) > thresh) bits |= 1ull << j;
+        // Exact early-out: if the centres are farther apart than the two half-diagonals plus the 1e-2 corner
+        // margin (with slack), no edge pair can intersect and no corner can pass check_in_box2d, so the
+        // reference's construction yields cnt == 0 -> overlap exactly 0 -> never > thresh (thresh >= 0).
+        const float ra = 0.5f * sqrtf(a[3] * a[3] + a[4] * a[4]);
+        for (int j = start; j < ncol; ++j) {
+            const float* b = sb + j * 7;
+            if (thresh >= 0.0f) {
+                const float dx = a[0] - b[0], dy = a[1] - b[1];
+                const float reach = (ra + 0.5f * sqrtf(b[3] * b[3] + b[4] * b[4])) * 1.001f + 0.05f;
+                if (dx * dx + dy * dy > reach * reach) continue;
+            }
+            if (rot_iou_bev(a, b) > thresh) bits |= 1ull << j;
+        }
     }
     mask[(int64_t)i * col_blocks + cb] = bits;
 }

@@ -1,14 +1,15 @@
 """Dense BEV head (a9): HeightCompression -> BaseBEVBackbone -> CenterHead decode.
 
 Mirrors models/backbones_2d/{height_compression.py:8-33, base_bev_backbone.py:9-115,
-center_head.py:29-98,251-276}.  The dense 2D convolutions are library GEMM-shaped work (cuDNN via
-torch, TF32 disabled for fp32 parity); in eval mode BatchNorm2d is folded into the convolution
-weights and ReLU applied in place.  The per-cell decode + sigmoid + class max is one CUDA kernel.
+center_head.py:29-98,251-276} (module tree / state_dict keys identical).  Inference path (eval mode):
+the whole head runs channels-last on this repository's tensor-core kernels -- sparse->dense scatter straight
+into NHWC, the 3x3 convs and the 2x2 transposed conv as 3xTF32 implicit GEMMs with BatchNorm folded into the
+weights and ReLU in the epilogue (insmos_conv2d_nhwc_tc), the two 1x1 heads as one fused linear kernel, and
+decode + sigmoid + class max in one kernel.  Training mode falls back to the plain torch modules.
 """
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 from insmos_b200 import ops
 
@@ -20,14 +21,21 @@ class HeightCompression(nn.Module):
         self.num_bev_features = model_cfg["NUM_BEV_FEATURES"]
 
     def forward(self, batch_dict):
-        dense = batch_dict["encoded_spconv_tensor"].dense()           # [1, C, D, H, W]
-        n, c, d, h, w = dense.shape
-        batch_dict["spatial_features"] = dense.view(n, c * d, h, w)
+        t = batch_dict["encoded_spconv_tensor"]
+        if self.training:
+            dense = t.dense()                                          # [1, C, D, H, W]
+            n, c, d, h, w = dense.shape
+            batch_dict["spatial_features"] = dense.view(n, c * d, h, w)
+        else:
+            D, H, W = t.spatial_shape
+            batch_dict["spatial_features_nhwc"] = (ops.dense_scatter_nhwc(t.features, t.indices, D, H, W), H, W)
+            batch_dict["spatial_features"] = None
         batch_dict["spatial_features_stride"] = batch_dict["encoded_spconv_tensor_stride"]
         return batch_dict
 
 
-def _fold_conv_bn(conv, bn, transposed=False):
+def _folded(conv, bn, transposed):
+    """[taps, Cin, Cout] weight with the eval-mode BatchNorm scale folded in, and the shift as bias (cached)."""
     ver = (conv.weight._version, bn.weight._version, bn.bias._version, bn.running_mean._version,
            bn.running_var._version, conv.weight.data_ptr(), bn.running_mean.data_ptr())
     cache = getattr(conv, "_insmos_folded", None)
@@ -35,8 +43,12 @@ def _fold_conv_bn(conv, bn, transposed=False):
         with torch.no_grad():
             scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
             shift = bn.bias - bn.running_mean * scale
-            w = conv.weight * (scale.view(1, -1, 1, 1) if transposed else scale.view(-1, 1, 1, 1))
-        cache = (ver, w.contiguous(), shift.contiguous())
+            if transposed:                                              # [Cin, Cout, kh, kw] -> [kh*kw, Cin, Cout]
+                w = conv.weight.permute(2, 3, 0, 1)
+            else:                                                       # [Cout, Cin, kh, kw] -> [kh*kw, Cin, Cout]
+                w = conv.weight.permute(2, 3, 1, 0)
+            w = (w * scale.view(1, 1, 1, -1)).reshape(-1, w.shape[2], w.shape[3]).contiguous()
+        cache = (ver, w, shift.contiguous())
         conv._insmos_folded = cache
     return cache[1], cache[2]
 
@@ -76,44 +88,48 @@ class BaseBEVBackbone(nn.Module):
                 bn2d(c_up), nn.ReLU()))
         self.num_bev_features = c_up
 
-    @staticmethod
-    def _run(seq, x, training):
-        if training:
-            return seq(x)
-        mods, i, pad = list(seq), 0, 0
+    def _fast_supported(self):
+        if len(self.blocks) != 1 or len(self.deblocks) != 1:
+            return False
+        mods = list(self.blocks[0])
+        convs = [m for m in mods if isinstance(m, nn.Conv2d)]
+        up = self.deblocks[0][0]
+        return (all(c.kernel_size == (3, 3) and c.stride == (1, 1) and c.in_channels % 32 == 0 and c.out_channels % 128 == 0
+                    for c in convs)
+                and isinstance(up, nn.ConvTranspose2d) and up.kernel_size == (2, 2) and up.stride == (2, 2)
+                and up.in_channels % 32 == 0 and up.out_channels % 128 == 0)
+
+    def forward_nhwc(self, x, H, W):
+        """x [H*W, C] channels-last -> ([2H*2W, C_up], 2H, 2W); the reference's layer sequence, fused."""
+        mods = list(self.blocks[0])
+        i = 0
         while i < len(mods):
             m = mods[i]
-            if isinstance(m, nn.ZeroPad2d):
-                pad = m.padding[0]
+            if isinstance(m, nn.Conv2d):
+                w, b = _folded(m, mods[i + 1], transposed=False)       # ZeroPad2d(1)+conv(p=0) == conv(p=1)
+                x = ops.conv2d_nhwc(x, H, W, w, 0, bias=b, relu=True)
+                i += 3
+            else:
                 i += 1
-                continue
-            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm2d):
-                tr = isinstance(m, nn.ConvTranspose2d)
-                w, b = _fold_conv_bn(m, mods[i + 1], transposed=tr)
-                if tr:
-                    x = F.conv_transpose2d(x, w, b, stride=m.stride)
-                else:
-                    x = F.conv2d(x, w, b, stride=m.stride, padding=(m.padding[0] + pad, m.padding[1] + pad))
-                pad = 0
-                i += 2
-                if i < len(mods) and isinstance(mods[i], nn.ReLU):
-                    x = torch.relu_(x)
-                    i += 1
-                continue
-            x = m(x)
-            i += 1
-        return x
+        up = self.deblocks[0]
+        w, b = _folded(up[0], up[1], transposed=True)
+        return ops.conv2d_nhwc(x, H, W, w, 2, bias=b, relu=True), 2 * H, 2 * W
 
     def forward(self, data_dict):
+        if not self.training and data_dict.get("current_bev_nhwc") is not None and self._fast_supported():
+            x, H, W = data_dict["current_bev_nhwc"]
+            data_dict["spatial_features_2d_nhwc"] = self.forward_nhwc(x, H, W)
+            data_dict["spatial_features_2d"] = None
+            return data_dict
         x0 = data_dict["current_bev"]
         x, ups = x0, []
         for i, blk in enumerate(self.blocks):
-            x = self._run(blk, x, self.training)
+            x = blk(x)
             data_dict["spatial_features_%dx" % int(x0.shape[2] / x.shape[2])] = x
-            ups.append(self._run(self.deblocks[i], x, self.training) if len(self.deblocks) > 0 else x)
+            ups.append(self.deblocks[i](x) if len(self.deblocks) > 0 else x)
         x = torch.cat(ups, dim=1) if len(ups) > 1 else ups[0]
         if len(self.deblocks) > len(self.blocks):
-            x = self._run(self.deblocks[-1], x, self.training)
+            x = self.deblocks[-1](x)
         data_dict["spatial_features_2d"] = x
         return data_dict
 
@@ -132,20 +148,41 @@ class CenterHead(nn.Module):
         self.conv_box = nn.Conv2d(input_channels, 8, kernel_size=1)
         nn.init.constant_(self.conv_cls.bias, -np.log((1 - 0.01) / 0.01))
         nn.init.normal_(self.conv_box.weight, mean=0, std=0.001)
+        self._heads = None
+
+    def _fused_heads(self):
+        """[Cin, ncls+8] weight and [ncls+8] bias of the two 1x1 heads, cached."""
+        ver = (self.conv_cls.weight._version, self.conv_box.weight._version, self.conv_cls.bias._version,
+               self.conv_box.bias._version, self.conv_cls.weight.data_ptr())
+        if self._heads is None or self._heads[0] != ver:
+            with torch.no_grad():
+                w = torch.cat([self.conv_cls.weight.flatten(1), self.conv_box.weight.flatten(1)], 0).t().contiguous()
+                b = torch.cat([self.conv_cls.bias, self.conv_box.bias]).contiguous()
+            self._heads = (ver, w, b)
+        return self._heads[1], self._heads[2]
 
     def forward(self, data_dict, Model_mode):
         if Model_mode == "train":
             raise NotImplementedError("CenterHead target assignment / losses are training-only (out of scope, SURVEY 8f N3)")
-        x = data_dict["spatial_features_2d"]
-        cls = self.conv_cls(x)                                         # [1, ncls, H, W]
-        box = self.conv_box(x)                                         # [1, 8, H, W]
-        if cls.shape[0] != 1:
-            raise NotImplementedError("batch 1 per sample (models.py:313)")
         t = self.target_cfg
-        boxes, scores, labels = ops.center_decode(cls[0], box[0], t["OUT_SIZE_FACTOR"], t["VOXEL_SIZE"][0],
-                                                  t["VOXEL_SIZE"][1], self.point_cloud_range[0], self.point_cloud_range[1])
-        data_dict["batch_cls_preds"] = cls[0].permute(1, 2, 0).reshape(1, -1, self.num_class)   # raw logits view
+        dec = (t["OUT_SIZE_FACTOR"], t["VOXEL_SIZE"][0], t["VOXEL_SIZE"][1], self.point_cloud_range[0], self.point_cloud_range[1])
+        nhwc = data_dict.get("spatial_features_2d_nhwc")
+        if nhwc is not None:
+            x, H, W = nhwc
+            w, b = self._fused_heads()
+            head = ops.linear(x, w, bias=b)                               # [H*W, ncls+8]
+            cls_v, box_v = head[:, :self.num_class], head[:, self.num_class:]
+            boxes, scores, labels = ops.center_decode(cls_v, box_v, *dec, hw=(H, W))
+            data_dict["batch_cls_preds"] = cls_v.unsqueeze(0)
+        else:
+            x = data_dict["spatial_features_2d"]
+            cls = self.conv_cls(x)                                         # [1, ncls, H, W]
+            box = self.conv_box(x)                                         # [1, 8, H, W]
+            if cls.shape[0] != 1:
+                raise NotImplementedError("batch 1 per sample (models.py:313)")
+            boxes, scores, labels = ops.center_decode(cls[0], box[0], *dec)
+            data_dict["batch_cls_preds"] = cls[0].permute(1, 2, 0).reshape(1, -1, self.num_class)
         data_dict["batch_box_preds"] = boxes.unsqueeze(0)
         data_dict["cls_preds_normalized"] = False
-        data_dict["_decoded"] = (boxes, scores, labels)                 # sigmoid / class max already done on device
+        data_dict["_decoded"] = (boxes, scores, labels)                     # sigmoid / class max already done on device
         return data_dict

@@ -148,7 +148,11 @@ class UNetV2(nn.Module):
 
         # ---- instance detection
         batch_dict = self.to_bev(batch_dict)
-        batch_dict["current_bev"] = batch_dict["spatial_features"][-1].unsqueeze(0)
+        if batch_dict.get("spatial_features") is not None:
+            batch_dict["current_bev"] = batch_dict["spatial_features"][-1].unsqueeze(0)
+            batch_dict["current_bev_nhwc"] = None
+        else:                                                               # eval: channels-last tensor-core path
+            batch_dict["current_bev_nhwc"] = batch_dict["spatial_features_nhwc"]
         batch_dict = self.bev_backbone(batch_dict)
         batch_dict = self.center_head(batch_dict, Model_mode)
         pred_dicts, recall_dicts = post_processing(batch_dict, self.post_process, self.num_class)

@@ -402,18 +402,51 @@ def dense_scatter(feat, coords, D, H, W):
 
 
 # ---- detection head -----------------------------------------------------------------------------
-def center_decode(cls, box, out_size_factor, vx, vy, x_min, y_min):
-    """cls [ncls,H,W], box [8,H,W] -> boxes [HW,7], scores [HW], labels [HW] i32 (1-based)."""
-    cls = _req(cls, F32, "center_decode")
-    box = _req(box, F32, "center_decode")
-    ncls, H, W = cls.shape
+def center_decode(cls, box, out_size_factor, vx, vy, x_min, y_min, hw=None):
+    """head outputs -> boxes [HW,7], scores [HW], labels [HW] i32 (1-based).
+    NCHW (hw=None): cls [ncls,H,W], box [8,H,W].  Channels-last (hw=(H,W)): cls [H*W,ncls], box [H*W,8] row-strided
+    views (e.g. column slices of one [H*W,11] head output)."""
+    if hw is None:
+        cls = _req(cls, F32, "center_decode")
+        box = _req(box, F32, "center_decode")
+        ncls, H, W = cls.shape
+        cs, ps, bcs, bps = H * W, 1, H * W, 1
+    else:
+        H, W = hw
+        assert cls.is_cuda and cls.dtype == F32 and box.dtype == F32 and cls.stride(1) == 1 and box.stride(1) == 1
+        ncls = cls.shape[1]
+        cs, ps, bcs, bps = 1, cls.stride(0), 1, box.stride(0)
     dev = cls.device
     boxes = torch.empty((H * W, 7), dtype=F32, device=dev)
     scores = torch.empty(H * W, dtype=F32, device=dev)
     labels = torch.empty(H * W, dtype=I32, device=dev)
-    call("insmos_center_decode", _p(cls), _p(box), ncls, H, W, float(out_size_factor), float(vx), float(vy),
-         float(x_min), float(y_min), _p(boxes), _p(scores), _p(labels), _stream())
+    call("insmos_center_decode", _p(cls), cs, ps, _p(box), bcs, bps, ncls, H, W, float(out_size_factor), float(vx),
+         float(vy), float(x_min), float(y_min), _p(boxes), _p(scores), _p(labels), _stream())
     return boxes, scores, labels
+
+
+def conv2d_nhwc(x, H, W, weight, mode, bias=None, relu=False):
+    """dense conv on tensor cores (3xTF32): x [H*W,Cin] channels-last, weight [taps,Cin,Cout] (BN folded).
+    mode 0: 3x3 pad 1; 1: 1x1; 2: 2x2 stride-2 transposed conv (output [2H*2W,Cout])."""
+    x = _req(x, F32, "conv2d_nhwc")
+    weight = _req(weight, F32, "conv2d_nhwc")
+    taps, Cin, Cout = weight.shape
+    assert x.shape == (H * W, Cin) and taps == (9, 1, 4)[mode]
+    out = torch.empty(((4 if mode == 2 else 1) * H * W, Cout), dtype=F32, device=x.device)
+    if bias is not None:
+        bias = _req(bias, F32, "conv2d_nhwc")
+    call("insmos_conv2d_nhwc_tc", _p(x), H, W, Cin, _p(weight), mode, Cout, _p(bias), 1 if relu else 0, _p(out), _stream())
+    return out
+
+
+def dense_scatter_nhwc(feat, coords, D, H, W):
+    """SparseConvTensor.dense() + HeightCompression, channels-last: [H*W, C*D] with channel c*D+z."""
+    feat = _req(feat, F32, "dense_scatter_nhwc")
+    coords = _req(coords, I32, "dense_scatter_nhwc")
+    n, Cc = feat.shape
+    out = torch.empty((H * W, Cc * D), dtype=F32, device=feat.device)
+    call("insmos_dense_scatter_nhwc", _p(feat), _p(coords), n, Cc, D, H, W, _p(out), _stream())
+    return out
 
 
 def nms_rotated(boxes_sorted, thresh, max_keep):

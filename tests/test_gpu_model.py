@@ -57,20 +57,30 @@ def _check_front(d, ref):
 
 def _check_discrete_stage_in_situ(d, pred):
     """oracle selection + C NMS on the GPU's own decoded candidates == the GPU's boxes (exact)."""
+    from insmos_b200 import ops
+    from test_gpu_detect import _keep_equal_or_explained
+    dev = d["_decoded"][0].device
     boxes, scores, labels = [t.cpu() for t in d["_decoded"]]
     mask = scores >= graph.PP["SCORE_THRESH"]
     s, b = scores[mask], boxes[mask]
-    sel = torch.zeros(0, dtype=torch.long)
-    if s.shape[0] > 0:
-        top_s, idx = torch.topk(s, k=min(graph.PP["NMS_PRE_MAXSIZE"], s.shape[0]))
-        order = top_s.sort(0, descending=True)[1]
-        keep = torch.from_numpy(native.nms(b[idx][order][:, :7].contiguous().numpy(), graph.PP["NMS_THRESH"]))
-        sel = mask.nonzero().view(-1)[idx[order[keep][:graph.PP["NMS_POST_MAXSIZE"]]]]
     got = pred["pred_boxes"].cpu()
-    assert got.shape[0] == sel.shape[0], "in-situ NMS kept %d, device kept %d" % (sel.shape[0], got.shape[0])
-    same = (got == boxes[sel]).all(dim=1).float().mean().item() if sel.numel() else 1.0
-    assert same >= 0.99, "device selection/NMS differs from the oracle on identical candidates (%.3f equal)" % same
-    assert torch.equal(pred["pred_labels"].cpu(), labels[sel].long()) or same < 1.0
+    if s.shape[0] == 0:
+        assert got.shape[0] == 0
+        return
+    top_s, idx = torch.topk(s, k=min(graph.PP["NMS_PRE_MAXSIZE"], s.shape[0]))
+    order = top_s.sort(0, descending=True)[1]
+    cand = b[idx][order][:, :7].contiguous()                     # the sorted candidate list both sides see
+    keep_o = native.nms(cand.numpy(), graph.PP["NMS_THRESH"])
+    keep_d = ops.nms_rotated(cand.to(dev), graph.PP["NMS_THRESH"], 1 << 20).cpu().numpy().astype(np.int64)
+    # identical inputs: keep lists equal, or the first divergence sits on an IoU within 1e-5 of the threshold
+    # (device libm vs glibc sin/cos/atan2 round differently in the last bit)
+    assert _keep_equal_or_explained(keep_d, keep_o, cand.numpy(), graph.PP["NMS_THRESH"]), (keep_d[:10], keep_o[:10])
+    # and the model's own output is exactly the device NMS applied to that list (selection plumbing)
+    sel = mask.nonzero().view(-1)[idx[order[torch.from_numpy(keep_d)][:graph.PP["NMS_POST_MAXSIZE"]]]]
+    assert got.shape[0] == sel.shape[0], "model kept %d boxes, stand-alone device NMS %d" % (got.shape[0], sel.shape[0])
+    same = (got == boxes[sel]).all(dim=1).float().mean().item()
+    assert same >= 0.99, "model selection differs from stand-alone device NMS on the same candidates (%.3f equal)" % same
+    assert same < 1.0 or torch.equal(pred["pred_labels"].cpu(), labels[sel].long())
 
 
 def _match_rate(a, b, tol=1e-3):
