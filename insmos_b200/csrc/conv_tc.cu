@@ -1,0 +1,261 @@
+// Sparse convolution, tensor-core path (3xTF32 on mma.sync m16n8k8), v3.
+//
+// Work decomposition as in v2 (one independent warp per (tile of TM output rows, group of NT n-tiles); bucket by
+// bucket; pairs of one bucket packed 16 at a time into the M dimension; accumulators of the tile in shared memory;
+// weights pre-arranged in fragment order, see insmos_conv_prep_weights in conv.cu).  What changed comes from the
+// ncu source page of v2 (profiles/r01_conv_v2_sass_notes.md): ~190 executed instructions per 16-pair chunk, 3 of
+// them HMMA.  v3 removes the bloat:
+//   * the TF32 hi/lo split of the gathered activations is hi = x & 0xffffe000, lo = x - hi (2 instructions; the
+//     tensor core ignores the low 13 mantissa bits of lo) instead of cvt.rna.tf32 (emulated, ~4 instr + NaN path);
+//   * channel counts that are multiples of 8 up to 48 are compile-time (KSC = Cin/8): no per-chunk 64-bit address
+//     arithmetic, fully unrolled k-steps;
+//   * the weight fragments of a bucket are loaded once per bucket and kept in registers across its chunks;
+//   * the next chunk's rule-book entries AND gathered feature rows are prefetched one full iteration ahead, so the
+//     two dependent global-load latencies overlap the current chunk's mma + shared-memory accumulate.
+// KSC == 0 is the generic path (any Cin, runtime k-step loop, 4 k-steps of loads in flight).
+#include "common.cuh"
+
+#define TC_WARPS 4
+
+__device__ __forceinline__ float tc_epilogue(float v, int c, int64_t row, int Cout, const insmos_epilogue_t& ep) {
+    if (ep.scale) v = __fmaf_rn(v, __ldg(ep.scale + c), __ldg(ep.shift + c));
+    if (ep.bias) v += __ldg(ep.bias + c);
+    if (ep.residual) v += __ldg(ep.residual + row * Cout + c);
+    if (ep.relu) v = fmaxf(v, 0.0f);
+    return v;
+}
+__device__ __forceinline__ void split_trunc(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));          // exact; low bits ignored by the tensor core
+}
+__device__ __forceinline__ void mma_tf32x(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct TcArgs {
+    const float* in; const uint4* wf; const uint16_t* seg; const uint32_t* entries; float* out;
+    int64_t n_out, n_tiles; int groups, Cin, Cout, K, TM, KS, NT8;
+    insmos_epilogue_t ep;
+};
+
+// chunk iterator over the non-empty buckets of one tile
+struct ChunkIt {
+    const int* sseg; int K, k, s0, n, c0;
+    __device__ __forceinline__ bool next() {
+        c0 += 16;
+        while (c0 >= n) {
+            if (++k >= K) return false;
+            s0 = sseg[k]; n = sseg[k + 1] - s0; c0 = 0;
+        }
+        return true;
+    }
+};
+
+template <int NT, int KSC>
+__global__ void __launch_bounds__(TC_WARPS * 32)
+k_spconv_tc3(TcArgs p) {
+    constexpr int CW = NT * 8;
+    constexpr int KSR = KSC > 0 ? KSC : 1;
+    extern __shared__ __align__(16) float sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t wglobal = (int64_t)blockIdx.x * TC_WARPS + warp;
+    const int64_t tile = wglobal / p.groups;
+    const int grp = (int)(wglobal - tile * p.groups);
+    if (tile >= p.n_tiles) return;                           // warps are independent: no block barrier below
+    const int TM = p.TM, K = p.K;
+    const int Cin = KSC > 0 ? KSC * 8 : p.Cin;
+    const int KS = KSC > 0 ? KSC : p.KS;
+    float* acc = sm + (size_t)warp * TM * CW;
+    int* sseg = reinterpret_cast<int*>(sm + (size_t)TC_WARPS * TM * CW) + warp * (K + 1);
+    {
+        const uint16_t* tseg = p.seg + tile * (K + 1);
+        for (int k = lane; k <= K; k += 32) sseg[k] = tseg[k];
+        for (int i = lane; i < TM * CW; i += 32) acc[i] = 0.0f;
+    }
+    __syncwarp();
+    const uint32_t* tent = p.entries + tile * (int64_t)TM * K;
+    const int nt0 = grp * NT;
+    const float* __restrict__ in = p.in;
+
+    // three-stage software pipeline over chunks: entries of chunk i+2 and gathered rows of chunk i+1 are in flight
+    // while chunk i is multiplied, so neither global-load latency sits on the critical path.
+    struct Ent { uint32_t lo, hi; int k; bool vlo, vhi, ok; };
+    ChunkIt it{sseg, K, -1, 0, 0, 0};
+    auto fetch = [&]() -> Ent {
+        Ent e; e.lo = 0u; e.hi = 0u; e.vlo = false; e.vhi = false;
+        e.ok = it.next(); e.k = it.k;
+        if (e.ok) {
+            e.vlo = (it.c0 + g) < it.n; e.vhi = (it.c0 + g + 8) < it.n;
+            if (e.vlo) e.lo = __ldg(tent + it.s0 + it.c0 + g);
+            if (e.vhi) e.hi = __ldg(tent + it.s0 + it.c0 + g + 8);
+        }
+        return e;
+    };
+    float2 rlo[KSR], rhi[KSR];                               // rows of the NEXT chunk (compile-time path)
+    auto load_rows = [&](const Ent& e) {
+        if (KSC > 0) {
+            const float* xl = in + (size_t)(e.lo & INSMOS_ROW_MASK) * (KSC * 8) + 2 * t;
+            const float* xh = in + (size_t)(e.hi & INSMOS_ROW_MASK) * (KSC * 8) + 2 * t;
+#pragma unroll
+            for (int ks = 0; ks < KSR; ++ks) {
+                rlo[ks] = e.vlo ? __ldg(reinterpret_cast<const float2*>(xl + ks * 8)) : make_float2(0.f, 0.f);
+                rhi[ks] = e.vhi ? __ldg(reinterpret_cast<const float2*>(xh + ks * 8)) : make_float2(0.f, 0.f);
+            }
+        }
+    };
+    Ent E0 = fetch();
+    Ent E1 = E0.ok ? fetch() : E0;
+    if (E0.ok) load_rows(E0);
+
+    int kb = -1;                                             // bucket whose weight fragments are in registers
+    uint4 bfrag[NT][KSR];
+    while (E0.ok) {
+        const int kc = E0.k;
+        const bool cv_lo = E0.vlo, cv_hi = E0.vhi;
+        const uint32_t ce_lo = E0.lo, ce_hi = E0.hi;
+        float2 clo[KSR], chi[KSR];
+#pragma unroll
+        for (int ks = 0; ks < KSR; ++ks) { clo[ks] = rlo[ks]; chi[ks] = rhi[ks]; }
+        Ent E2 = E1.ok ? fetch() : E1;                       // entries of chunk i+2
+        if (E1.ok) load_rows(E1);                            // rows of chunk i+1 (its entries arrived last iteration)
+        float d[NT][4];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) { d[j][0] = d[j][1] = d[j][2] = d[j][3] = 0.0f; }
+
+        if (KSC > 0) {
+            if (kc != kb) {                                  // new bucket: fetch its weight fragments once
+                const uint4* wk = p.wf + ((int64_t)kc * p.NT8 + nt0) * KSC * 32 + lane;
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int ks = 0; ks < KSR; ++ks) bfrag[j][ks] = __ldg(wk + (j * KSC + ks) * 32);
+                kb = kc;
+            }
+#pragma unroll
+            for (int ks = 0; ks < KSR; ++ks) {
+                uint32_t ah[4], al[4];
+                split_trunc(clo[ks].x, ah[0], al[0]); split_trunc(chi[ks].x, ah[1], al[1]);
+                split_trunc(clo[ks].y, ah[2], al[2]); split_trunc(chi[ks].y, ah[3], al[3]);
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    mma_tf32x(d[j], al, bfrag[j][ks].x, bfrag[j][ks].y);
+                    mma_tf32x(d[j], ah, bfrag[j][ks].z, bfrag[j][ks].w);
+                    mma_tf32x(d[j], ah, bfrag[j][ks].x, bfrag[j][ks].y);
+                }
+            }
+        } else {
+            const bool even = (Cin & 1) == 0;
+            const float* x_lo = in + (size_t)(ce_lo & INSMOS_ROW_MASK) * Cin;
+            const float* x_hi = in + (size_t)(ce_hi & INSMOS_ROW_MASK) * Cin;
+            const uint4* wk = p.wf + ((int64_t)kc * p.NT8 + nt0) * KS * 32 + lane;
+#pragma unroll 4
+            for (int ks = 0; ks < KS; ++ks) {
+                const int col = ks * 8 + 2 * t;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // (g,2t) (g+8,2t) (g,2t+1) (g+8,2t+1)
+                if (even) {
+                    if (col < Cin) {
+                        if (cv_lo) { const float2 v = __ldg(reinterpret_cast<const float2*>(x_lo + col)); a0 = v.x; a2 = v.y; }
+                        if (cv_hi) { const float2 v = __ldg(reinterpret_cast<const float2*>(x_hi + col)); a1 = v.x; a3 = v.y; }
+                    }
+                } else {
+                    if (col < Cin) { if (cv_lo) a0 = __ldg(x_lo + col); if (cv_hi) a1 = __ldg(x_hi + col); }
+                    if (col + 1 < Cin) { if (cv_lo) a2 = __ldg(x_lo + col + 1); if (cv_hi) a3 = __ldg(x_hi + col + 1); }
+                }
+                uint4 b[NT];
+#pragma unroll
+                for (int j = 0; j < NT; ++j) b[j] = __ldg(wk + ((int64_t)j * KS + ks) * 32);
+                uint32_t ah[4], al[4];
+                split_trunc(a0, ah[0], al[0]); split_trunc(a1, ah[1], al[1]);
+                split_trunc(a2, ah[2], al[2]); split_trunc(a3, ah[3], al[3]);
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    mma_tf32x(d[j], al, b[j].x, b[j].y);
+                    mma_tf32x(d[j], ah, b[j].z, b[j].w);
+                    mma_tf32x(d[j], ah, b[j].x, b[j].y);
+                }
+            }
+        }
+        // accumulate into the tile (within a bucket every output row occurs once: plain read-modify-write)
+        const int r_lo = (int)(ce_lo >> INSMOS_ROW_BITS) * CW + 2 * t;
+        const int r_hi = (int)(ce_hi >> INSMOS_ROW_BITS) * CW + 2 * t;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            if (cv_lo) {
+                float2* q = reinterpret_cast<float2*>(acc + r_lo + j * 8);
+                float2 v = *q; v.x += d[j][0]; v.y += d[j][1]; *q = v;
+            }
+            if (cv_hi) {
+                float2* q = reinterpret_cast<float2*>(acc + r_hi + j * 8);
+                float2 v = *q; v.x += d[j][2]; v.y += d[j][3]; *q = v;
+            }
+        }
+        __syncwarp();
+        E0 = E1; E1 = E2;
+    }
+    const int64_t row0 = tile * TM;
+    const int rows = (int)((p.n_out - row0) < TM ? (p.n_out - row0) : TM);
+    const int cbase = nt0 * 8;
+    for (int i = lane; i < rows * CW; i += 32) {
+        const int r = i / CW, c = cbase + (i % CW);
+        if (c < p.Cout) p.out[(row0 + r) * p.Cout + c] = tc_epilogue(acc[i], c, row0 + r, p.Cout, p.ep);
+    }
+}
+
+template <int NT, int KSC>
+static int launch_tc3(const TcArgs& a, cudaStream_t st) {
+    const size_t smem = sizeof(float) * (size_t)TC_WARPS * a.TM * NT * 8 + sizeof(int) * (size_t)TC_WARPS * (a.K + 1);
+    if (smem > 220 * 1024) return INSMOS_ERR_UNSUPPORTED;
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_spconv_tc3<NT, KSC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int64_t warps = a.n_tiles * a.groups;
+    k_spconv_tc3<NT, KSC><<<(unsigned)ceil_div64(warps, TC_WARPS), TC_WARPS * 32, smem, st>>>(a);
+    INSMOS_CHECK_LAUNCH("k_spconv_tc3");
+    return INSMOS_OK;
+}
+
+template <int NT>
+static int dispatch_ks(const TcArgs& a, cudaStream_t st) {
+    if (a.Cin % 8 == 0) {
+        switch (a.Cin / 8) {
+            case 1: return launch_tc3<NT, 1>(a, st);
+            case 2: return launch_tc3<NT, 2>(a, st);
+            case 3: return launch_tc3<NT, 3>(a, st);
+            case 4: return launch_tc3<NT, 4>(a, st);
+            case 6: return launch_tc3<NT, 6>(a, st);
+            default: break;
+        }
+    }
+    return launch_tc3<NT, 0>(a, st);
+}
+
+extern "C" int insmos_sparse_conv_fwd_tc(const float* in, int64_t n_in, int32_t Cin,
+                                         const void* wfrag, int32_t K, int32_t Cout,
+                                         const uint16_t* seg, const uint32_t* entries, int32_t TM,
+                                         float* out, int64_t n_out,
+                                         const insmos_epilogue_t* ep_in, void* stream) {
+    if ((n_in > 0 && !in) || !wfrag || !seg || !entries || (n_out > 0 && !out) || Cin <= 0 || Cout <= 0 || K <= 0 || n_out < 0 || n_in < 0)
+        return INSMOS_ERR_INVALID_ARG;
+    if (TM != 16 && TM != 32 && TM != 64 && TM != 128) return INSMOS_ERR_INVALID_ARG;
+    if (n_in > (int64_t)INSMOS_ROW_MASK + 1) return INSMOS_ERR_UNSUPPORTED;
+    TcArgs a;
+    a.in = in; a.wf = (const uint4*)wfrag; a.seg = seg; a.entries = entries; a.out = out;
+    a.n_out = n_out; a.n_tiles = ceil_div64(n_out, TM);
+    a.Cin = Cin; a.Cout = Cout; a.K = K; a.TM = TM; a.KS = (Cin + 7) / 8; a.NT8 = (Cout + 7) / 8;
+    a.ep = insmos_epilogue_t{nullptr, nullptr, nullptr, nullptr, 0};
+    if (ep_in) a.ep = *ep_in;
+    if (a.ep.scale && !a.ep.shift) return INSMOS_ERR_INVALID_ARG;
+    if (n_out == 0) return INSMOS_OK;
+    // two n-tiles per warp halve the redundant gathers; only when that still leaves thousands of warps
+    if (a.NT8 % 2 == 0 && a.n_tiles * (a.NT8 / 2) >= 4096) {
+        a.groups = a.NT8 / 2;
+        return dispatch_ks<2>(a, (cudaStream_t)stream);
+    }
+    a.groups = a.NT8;
+    return dispatch_ks<1>(a, (cudaStream_t)stream);
+}

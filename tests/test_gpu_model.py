@@ -60,16 +60,19 @@ def _check_discrete_stage_in_situ(d, pred):
     from insmos_b200 import ops
     from test_gpu_detect import _keep_equal_or_explained
     dev = d["_decoded"][0].device
-    boxes, scores, labels = [t.cpu() for t in d["_decoded"]]
-    mask = scores >= graph.PP["SCORE_THRESH"]
-    s, b = scores[mask], boxes[mask]
+    # the candidate order is computed ON THE DEVICE with the same torch ops as the model: empty BEV cells
+    # produce exactly equal scores and torch's tie order differs between its CPU and CUDA sorts
+    boxes_d, scores_d, labels_d = d["_decoded"]
+    mask_d = scores_d >= graph.PP["SCORE_THRESH"]
     got = pred["pred_boxes"].cpu()
-    if s.shape[0] == 0:
+    if int(mask_d.sum()) == 0:
         assert got.shape[0] == 0
         return
-    top_s, idx = torch.topk(s, k=min(graph.PP["NMS_PRE_MAXSIZE"], s.shape[0]))
-    order = top_s.sort(0, descending=True)[1]
-    cand = b[idx][order][:, :7].contiguous()                     # the sorted candidate list both sides see
+    top_s, idx_d = torch.topk(scores_d[mask_d], k=min(graph.PP["NMS_PRE_MAXSIZE"], int(mask_d.sum())))
+    order_d = top_s.sort(0, descending=True)[1]
+    boxes, labels = boxes_d.cpu(), labels_d.cpu()
+    mask, idx, order = mask_d.cpu(), idx_d.cpu(), order_d.cpu()
+    cand = boxes[mask][idx][order][:, :7].contiguous()           # the sorted candidate list both sides see
     keep_o = native.nms(cand.numpy(), graph.PP["NMS_THRESH"])
     keep_d = ops.nms_rotated(cand.to(dev), graph.PP["NMS_THRESH"], 1 << 20).cpu().numpy().astype(np.int64)
     # identical inputs: keep lists equal, or the first divergence sits on an IoU within 1e-5 of the threshold
