@@ -42,11 +42,15 @@ __device__ __forceinline__ uint64_t pack_key(int b, int c0, int c1, int c2, int 
            ((uint64_t)(uint32_t)(c2 + 32768) << 32) | ((uint64_t)(uint32_t)(c3 + 128) << 48) |
            ((uint64_t)(uint32_t)b << 56);
 }
+// 64-bit key -> 32-bit slot hash, all 32-bit integer ops (the rule-book build is instruction bound on this:
+// profiles/r01_conv_v2_sass_notes.md).  Two odd multipliers on the halves + xorshift-multiply finalisers.
 __device__ __forceinline__ uint64_t hash64(uint64_t k) {
-    k ^= k >> 33; k *= 0xff51afd7ed558ccdull;
-    k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull;
-    k ^= k >> 33;
-    return k;
+    uint32_t lo = (uint32_t)k, hi = (uint32_t)(k >> 32);
+    uint32_t h = lo * 0x9E3779B1u ^ hi * 0x85EBCA77u;
+    h ^= h >> 15; h *= 0x2C1B3C6Du;
+    h ^= h >> 12; h *= 0x297A2D39u;
+    h ^= h >> 15;
+    return (uint64_t)h;
 }
 
 // insert (or find) key; returns slot index. Table load factor <= 0.5 guarantees termination.

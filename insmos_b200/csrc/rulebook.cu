@@ -1,6 +1,6 @@
 // Rule-book (kernel map / indice pair) construction.  SURVEY.md section 8 rows a4, a8, a12.
 //
-// Layout is output-stationary and tiled for the convolution kernels in conv.cu:
+// Layout is output-stationary and tiled for the convolution kernels in conv.cu / conv_tc.cu:
 //   * output rows are cut into tiles of TM consecutive rows,
 //   * tile t owns the fixed slab entries[t*TM*K, (t+1)*TM*K) -- no global scan, no atomics, the
 //     layout is a pure function of the inputs (deterministic); only the occupied prefix of a slab
@@ -12,6 +12,10 @@
 //   * entry = (out_row_in_tile << 25) | in_row.
 // One block builds one tile: TM*K hash probes (16-byte slot loads, L2 resident table) staged in
 // shared memory, then one warp per offset compacts its bucket with ballots.
+//
+// The probe loop is instruction bound (ncu: profiles/r01_conv_v2_sass_notes.md), so it is kept minimal:
+// the packed 64-bit key is LINEAR in the coordinates, hence key(in) = key(row base) + delta[k] with a per-offset
+// delta precomputed once per block; lanes run over offsets (no division), rows over warps.
 #include "common.cuh"
 
 #define RB_THREADS 256
@@ -21,69 +25,108 @@ extern "C" int64_t insmos_rulebook_entries_capacity(int64_t n_out, int32_t K, in
     return ceil_div64(n_out, TM) * (int64_t)TM * K;
 }
 
+// coordinates may move by at most this many voxels through a kernel offset; rows whose base coordinate is closer
+// than this to the edge of the packable range take the checked slow path
+#define RB_GUARD 512
+
+__device__ __forceinline__ int64_t packed_delta(int d0, int d1, int d2, int d3) {
+    return (int64_t)d0 + (int64_t)d1 * 65536ll + (int64_t)d2 * 4294967296ll + (int64_t)d3 * 281474976710656ll;
+}
+
 __global__ void __launch_bounds__(RB_THREADS)
 k_rulebook_tiles(const int32_t* __restrict__ out_coords, int64_t n_out,
                  const insmos_slot_t* __restrict__ table, uint64_t mask,
                  insmos_mapspec_t spec, int TM,
                  uint16_t* __restrict__ seg, uint32_t* __restrict__ entries,
                  unsigned long long* pair_count) {
-    extern __shared__ int smem[];
+    extern __shared__ __align__(16) int smem[];
     const int K = spec.K, ncol = spec.ncol, ndim = spec.ndim;
-    int* nbr = smem;                       // [TM*K] in-row or -1
-    int* tc = nbr + TM * K;                // [TM*5] coordinates of the tile's rows
-    int* kd = tc + TM * 5;                 // [K*4]  per-offset per-dim term
-    int* hist = kd + K * 4;                // [K+1]
+    int* nbr = smem;                                            // [TM*K] in-row or -1
+    int64_t* delta = reinterpret_cast<int64_t*>(nbr + ((TM * K + 1) & ~1));   // [K] packed key delta of offset k
+    int64_t* rbase = delta + K;                                 // [TM] packed base key of the row (or -1)
+    int* kd = reinterpret_cast<int*>(rbase + TM);               // [K*4] per-offset digits/terms (slow path)
+    int* tc = kd + K * 4;                                       // [TM*5] coordinates of the tile's rows
+    int* hist = tc + TM * 5;                                    // [K+1]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = RB_THREADS / 32;
     const int64_t tile = blockIdx.x;
     const int64_t row0 = tile * TM;
+    const bool fast = (spec.mode == 0) && spec.q[0] == 1 && spec.q[1] == 1 && spec.q[2] == 1 && spec.q[3] == 1;
 
     for (int i = tid; i < TM * ncol; i += RB_THREADS) {
-        const int64_t g = row0 * ncol + i;
-        tc[(i / ncol) * 5 + (i % ncol)] = (g < n_out * ncol) ? out_coords[g] : 0;
+        const int64_t gi = row0 * ncol + i;
+        tc[(i / ncol) * 5 + (i % ncol)] = (gi < n_out * ncol) ? out_coords[gi] : 0;
     }
     for (int k = tid; k < K; k += RB_THREADS) {
         int rem = k;
         int dig[4] = {0, 0, 0, 0};
         if (spec.first_fastest) { for (int d = 0; d < ndim; ++d) { dig[d] = rem % spec.ksize[d]; rem /= spec.ksize[d]; } }
         else { for (int d = ndim - 1; d >= 0; --d) { dig[d] = rem % spec.ksize[d]; rem /= spec.ksize[d]; } }
-        for (int d = 0; d < 4; ++d)
-            kd[k * 4 + d] = (d < ndim) ? (spec.mode == 0 ? spec.b[d] + dig[d] * spec.e[d] : dig[d]) : 0;
+        int term[4];
+        for (int d = 0; d < 4; ++d) {
+            term[d] = (d < ndim) ? (spec.mode == 0 ? dig[d] * spec.e[d] : dig[d]) : 0;
+            kd[k * 4 + d] = (d < ndim && spec.mode == 0) ? spec.b[d] + term[d] : term[d];
+        }
+        delta[k] = packed_delta(term[0], term[1], term[2], term[3]);
     }
     __syncthreads();
+    if (fast) {                                                  // base key of every row: pack(c*a + b)
+        for (int r = tid; r < TM; r += RB_THREADS) {
+            int64_t key = -1;
+            if (row0 + r < n_out) {
+                const int* c = tc + r * 5;
+                int cb[4] = {0, 0, 0, 0};
+                bool ok = true;
+                for (int d = 0; d < 4; ++d)
+                    if (d < ndim) {
+                        cb[d] = c[1 + d] * spec.a[d] + spec.b[d];
+                        const int lim = (d == 3) ? 128 - 16 : 32768 - RB_GUARD;
+                        ok = ok && (cb[d] > -lim) && (cb[d] < lim);
+                    }
+                if (ok && (unsigned)c[0] < 128u) key = (int64_t)pack_key(c[0], cb[0], cb[1], cb[2], cb[3]);   // >= 0
+                else key = -2;                                   // in range only with per-probe checks: slow path
+            }
+            rbase[r] = key;
+        }
+        __syncthreads();
+    }
 
-    // ---- phase A: probe
-    const int total = TM * K;
-    for (int idx = tid; idx < total; idx += RB_THREADS) {
-        const int r = idx / K, k = idx - r * K;
-        int res = -1;
-        if (row0 + r < n_out) {
-            const int* c = tc + r * 5;
-            int ci[4] = {0, 0, 0, 0};
-            bool ok = true;
-            if (spec.mode == 0) {
+    // ---- phase A: probe.  Lanes run over offsets, warps over rows.
+    for (int r = warp; r < TM; r += nwarps) {
+        const bool row_ok = (row0 + r) < n_out;
+        const int64_t base = fast ? rbase[r] : -2;
+        for (int k = lane; k < K; k += 32) {
+            int res = -1;
+            if (row_ok) {
+                if (base >= 0) {
+                    res = table_find_row(table, mask, (uint64_t)(base + delta[k]));
+                } else if (base == -2) {                         // checked path (also: strided/inverse/transposed maps)
+                    const int* c = tc + r * 5;
+                    int ci[4] = {0, 0, 0, 0};
+                    bool ok = true;
+                    if (spec.mode == 0) {
 #pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    if (d < ndim) {
-                        int v = c[1 + d] * spec.a[d] + kd[k * 4 + d];
-                        const int q = spec.q[d];
-                        if (q > 1) { if (v % q) ok = false; v /= q; }
-                        ci[d] = v;
-                    }
-                }
-            } else {
+                        for (int d = 0; d < 4; ++d)
+                            if (d < ndim) {
+                                int v = c[1 + d] * spec.a[d] + kd[k * 4 + d];
+                                const int q = spec.q[d];
+                                if (q > 1) { if (v % q) ok = false; v /= q; }
+                                ci[d] = v;
+                            }
+                    } else {
 #pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    if (d < ndim) {
-                        const int base = floor_div(c[1 + d], spec.up_q[d]) * spec.up_q[d];
-                        if ((c[1 + d] - base) / spec.up_ts[d] != kd[k * 4 + d]) ok = false;
-                        ci[d] = base;
+                        for (int d = 0; d < 4; ++d)
+                            if (d < ndim) {
+                                const int b0 = floor_div(c[1 + d], spec.up_q[d]) * spec.up_q[d];
+                                if ((c[1 + d] - b0) / spec.up_ts[d] != kd[k * 4 + d]) ok = false;
+                                ci[d] = b0;
+                            }
                     }
+                    if (ok && coord_in_range(c[0], ci[0], ci[1], ci[2], ci[3]))
+                        res = table_find_row(table, mask, pack_key(c[0], ci[0], ci[1], ci[2], ci[3]));
                 }
             }
-            if (ok && coord_in_range(c[0], ci[0], ci[1], ci[2], ci[3]))
-                res = table_find_row(table, mask, pack_key(c[0], ci[0], ci[1], ci[2], ci[3]));
+            nbr[r * K + k] = res;
         }
-        nbr[idx] = res;
     }
     __syncthreads();
 
@@ -148,12 +191,15 @@ extern "C" int insmos_rulebook_build(const int32_t* out_coords, int64_t n_out,
     for (int d = 0; d < spec->ndim; ++d) {
         if (spec->ksize[d] < 1) return INSMOS_ERR_INVALID_ARG;
         if (spec->mode == 0 && spec->q[d] < 1) return INSMOS_ERR_INVALID_ARG;
+        if (spec->mode == 0 && (spec->ksize[d] - 1) * (spec->e[d] < 0 ? -spec->e[d] : spec->e[d]) >= (d == 3 ? 16 : RB_GUARD / 2))
+            return INSMOS_ERR_UNSUPPORTED;
         if (spec->mode == 1 && (spec->up_q[d] < 1 || spec->up_ts[d] < 1)) return INSMOS_ERR_INVALID_ARG;
         kprod *= spec->ksize[d];
     }
     if (kprod != spec->K) return INSMOS_ERR_INVALID_ARG;
     if (n_out == 0) return INSMOS_OK;
-    const size_t smem = sizeof(int) * ((size_t)TM * spec->K + (size_t)TM * 5 + (size_t)spec->K * 4 + spec->K + 1);
+    const size_t smem = sizeof(int) * (((size_t)TM * spec->K + 1) & ~(size_t)1) + sizeof(int64_t) * ((size_t)spec->K + TM) +
+                        sizeof(int) * ((size_t)spec->K * 4 + (size_t)TM * 5 + spec->K + 1);
     if (smem > 220 * 1024) return INSMOS_ERR_UNSUPPORTED;
     static thread_local size_t configured = 0;
     if (smem > configured) {
