@@ -14,6 +14,7 @@
 //     two dependent global-load latencies overlap the current chunk's mma + shared-memory accumulate.
 // KSC == 0 is the generic path (any Cin, runtime k-step loop, 4 k-steps of loads in flight).
 #include "common.cuh"
+#include <stdlib.h>
 
 #define TC_WARPS 4
 
@@ -207,6 +208,125 @@ k_spconv_tc3(TcArgs p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Large-channel layers (Cout >= 32): block-cooperative variant.
+// With one warp per (tile, 8-channel group) the [Cin x 8] weight fragments of every bucket are re-fetched by
+// every warp: for 128->128, K=27 on 6 k rows that is ~1.3 GB of L2->SM traffic per layer (measured 363 us).
+// Here a block of 8 warps owns a SUPER-TILE (G consecutive rule-book tiles, ~128 rows) x a slice of NT n-tiles;
+// per bucket the slice's weight fragments (contiguous in the fragment-ordered array) are staged ONCE in shared
+// memory, the bucket's 16-pair chunks are dealt round-robin to the warps, each warp gathers its rows once and
+// multiplies them against all NT n-tiles.  Chunks of one bucket touch distinct output rows, so the shared
+// accumulator needs no atomics; a block barrier separates buckets.
+#define BIG_WARPS 8
+template <int NT>
+__global__ void __launch_bounds__(BIG_WARPS * 32)
+k_spconv_tc_big(TcArgs p, int G, int n_slices) {
+    constexpr int CN = NT * 8;
+    extern __shared__ __align__(16) float sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t stile = blockIdx.x / n_slices;
+    const int slice = (int)(blockIdx.x - stile * n_slices);
+    const int TM = p.TM, K = p.K, KS = p.KS, Cin = p.Cin;
+    const int64_t tile0 = stile * G;
+    const int ntile = (int)((p.n_tiles - tile0) < G ? (p.n_tiles - tile0) : G);
+    const int nt0 = slice * NT;
+    float* acc = sm;                                                    // [G*TM][CN]
+    uint4* wbuf = reinterpret_cast<uint4*>(acc + (size_t)G * TM * CN);   // [NT][KS][32]
+    int* ssegs = reinterpret_cast<int*>(wbuf + (size_t)NT * KS * 32);    // [G][K+1]
+    for (int i = threadIdx.x; i < G * (K + 1); i += BIG_WARPS * 32) {
+        const int gi = i / (K + 1), k = i - gi * (K + 1);
+        ssegs[i] = (gi < ntile) ? p.seg[(tile0 + gi) * (K + 1) + k] : 0;
+    }
+    for (int i = threadIdx.x; i < G * TM * CN; i += BIG_WARPS * 32) acc[i] = 0.0f;
+    __syncthreads();
+    const bool even = (Cin & 1) == 0;
+    const float* __restrict__ in = p.in;
+    const int wn = NT * KS * 32;                                         // uint4 per weight slice
+    for (int k = 0; k < K; ++k) {
+        int tot = 0;
+        for (int gi = 0; gi < ntile; ++gi) tot += ssegs[gi * (K + 1) + k + 1] - ssegs[gi * (K + 1) + k];
+        if (tot == 0) continue;                                          // uniform across the block
+        const uint4* wk = p.wf + ((int64_t)k * p.NT8 + nt0) * KS * 32;
+        for (int i = threadIdx.x; i < wn; i += BIG_WARPS * 32) wbuf[i] = __ldg(wk + i);
+        __syncthreads();
+        int cid = 0;
+        for (int gi = 0; gi < ntile; ++gi) {
+            const int s0 = ssegs[gi * (K + 1) + k], n = ssegs[gi * (K + 1) + k + 1] - s0;
+            const uint32_t* tent = p.entries + (tile0 + gi) * (int64_t)TM * K + s0;
+            for (int c0 = 0; c0 < n; c0 += 16, ++cid) {
+                if ((cid & (BIG_WARPS - 1)) != warp) continue;
+                const bool v_lo = (c0 + g) < n, v_hi = (c0 + g + 8) < n;
+                const uint32_t e_lo = v_lo ? __ldg(tent + c0 + g) : 0u;
+                const uint32_t e_hi = v_hi ? __ldg(tent + c0 + g + 8) : 0u;
+                const float* x_lo = in + (size_t)(e_lo & INSMOS_ROW_MASK) * Cin;
+                const float* x_hi = in + (size_t)(e_hi & INSMOS_ROW_MASK) * Cin;
+                float d[NT][4];
+#pragma unroll
+                for (int j = 0; j < NT; ++j) { d[j][0] = d[j][1] = d[j][2] = d[j][3] = 0.0f; }
+#pragma unroll 4
+                for (int ks = 0; ks < KS; ++ks) {
+                    const int col = ks * 8 + 2 * t;
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                    if (even) {
+                        if (col < Cin) {
+                            if (v_lo) { const float2 v = __ldg(reinterpret_cast<const float2*>(x_lo + col)); a0 = v.x; a2 = v.y; }
+                            if (v_hi) { const float2 v = __ldg(reinterpret_cast<const float2*>(x_hi + col)); a1 = v.x; a3 = v.y; }
+                        }
+                    } else {
+                        if (col < Cin) { if (v_lo) a0 = __ldg(x_lo + col); if (v_hi) a1 = __ldg(x_hi + col); }
+                        if (col + 1 < Cin) { if (v_lo) a2 = __ldg(x_lo + col + 1); if (v_hi) a3 = __ldg(x_hi + col + 1); }
+                    }
+                    uint32_t ah[4], al[4];
+                    split_trunc(a0, ah[0], al[0]); split_trunc(a1, ah[1], al[1]);
+                    split_trunc(a2, ah[2], al[2]); split_trunc(a3, ah[3], al[3]);
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const uint4 b = wbuf[(j * KS + ks) * 32 + lane];
+                        mma_tf32x(d[j], al, b.x, b.y);
+                        mma_tf32x(d[j], ah, b.z, b.w);
+                        mma_tf32x(d[j], ah, b.x, b.y);
+                    }
+                }
+                const int r_lo = (gi * TM + (int)(e_lo >> INSMOS_ROW_BITS)) * CN + 2 * t;
+                const int r_hi = (gi * TM + (int)(e_hi >> INSMOS_ROW_BITS)) * CN + 2 * t;
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    if (v_lo) { float2* q = reinterpret_cast<float2*>(acc + r_lo + j * 8); float2 v = *q; v.x += d[j][0]; v.y += d[j][1]; *q = v; }
+                    if (v_hi) { float2* q = reinterpret_cast<float2*>(acc + r_hi + j * 8); float2 v = *q; v.x += d[j][2]; v.y += d[j][3]; *q = v; }
+                }
+            }
+        }
+        __syncthreads();                                                 // bucket done: acc rows + wbuf reusable
+    }
+    const int64_t row0 = tile0 * TM;
+    const int64_t rows_left = p.n_out - row0;
+    const int rows = (int)(rows_left < (int64_t)G * TM ? rows_left : (int64_t)G * TM);
+    const int cbase = nt0 * 8;
+    for (int i = threadIdx.x; i < rows * CN; i += BIG_WARPS * 32) {
+        const int r = i / CN, c = cbase + (i % CN);
+        if (c < p.Cout) p.out[(row0 + r) * p.Cout + c] = tc_epilogue(acc[i], c, row0 + r, p.Cout, p.ep);
+    }
+}
+
+static int launch_tc_big(const TcArgs& a, cudaStream_t st) {
+    constexpr int NT = 4;
+    int G = 128 / a.TM; if (G < 1) G = 1;
+    const int n_slices = (a.NT8 + NT - 1) / NT;
+    const size_t smem = sizeof(float) * (size_t)G * a.TM * NT * 8 + sizeof(uint4) * (size_t)NT * a.KS * 32 +
+                        sizeof(int) * (size_t)G * (a.K + 1);
+    if (smem > 220 * 1024) return INSMOS_ERR_UNSUPPORTED;
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_spconv_tc_big<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int64_t stiles = ceil_div64(a.n_tiles, G);
+    k_spconv_tc_big<NT><<<(unsigned)(stiles * n_slices), BIG_WARPS * 32, smem, st>>>(a, G, n_slices);
+    INSMOS_CHECK_LAUNCH("k_spconv_tc_big");
+    return INSMOS_OK;
+}
+
 template <int NT, int KSC>
 static int launch_tc3(const TcArgs& a, cudaStream_t st) {
     const size_t smem = sizeof(float) * (size_t)TC_WARPS * a.TM * NT * 8 + sizeof(int) * (size_t)TC_WARPS * (a.K + 1);
@@ -254,6 +374,9 @@ extern "C" int insmos_sparse_conv_fwd_tc(const float* in, int64_t n_in, int32_t 
     if (ep_in) a.ep = *ep_in;
     if (a.ep.scale && !a.ep.shift) return INSMOS_ERR_INVALID_ARG;
     if (n_out == 0) return INSMOS_OK;
+    a.groups = a.NT8;
+    // >= 32 output channels: weight traffic dominates -> block-cooperative kernel with the slice's weights in smem
+    if (a.NT8 >= 4 && getenv("INSMOS_NO_BIG") == nullptr) return launch_tc_big(a, (cudaStream_t)stream);
     // two n-tiles per warp halve the redundant gathers; only when that still leaves thousands of warps
     if (a.NT8 % 2 == 0 && a.n_tiles * (a.NT8 / 2) >= 4096) {
         a.groups = a.NT8 / 2;

@@ -212,13 +212,26 @@ k_nms_sweep(const unsigned long long* __restrict__ mask, int n, int max_keep, in
         if (s_num >= max_keep) break;
         unsigned long long kept = s_kept;
         while (kept) {
-            const int i = __ffsll((long long)kept) - 1;
-            kept &= kept - 1;
-            const unsigned long long* row = mask + (int64_t)(base + i) * col_blocks;
+            // up to 8 kept rows per step: all loads are issued before any is consumed (one L2 round trip per batch
+            // instead of one per kept box)
+            int idx[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                idx[u] = kept ? (__ffsll((long long)kept) - 1) : -1;
+                kept &= kept - 1;
+            }
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
                 const int c = tid + 64 * w;
-                if (c > blk && c < col_blocks) remv_w[w] |= row[c];
+                if (c > blk && c < col_blocks) {
+                    unsigned long long v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = (idx[u] >= 0) ? mask[(int64_t)(base + idx[u]) * col_blocks + c] : 0ull;
+                    unsigned long long o = 0ull;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) o |= v[u];
+                    remv_w[w] |= o;
+                }
             }
         }
         __syncthreads();
