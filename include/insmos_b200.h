@@ -171,6 +171,14 @@ int insmos_sparse_conv_fwd(const float* in, int64_t n_in, int32_t Cin,
                            float* out, int64_t n_out,
                            const insmos_epilogue_t* ep, int32_t algo, void* stream);
 
+/* Default path of the same convolution: exact fp32 FFMA, one thread per rule-book pair with register-blocked
+ * outputs (conv_ffma.cu).  Requires Cout % 4 == 0; returns INSMOS_ERR_UNSUPPORTED otherwise. */
+int insmos_sparse_conv_fwd_ffma(const float* in, int64_t n_in, int32_t Cin,
+                                const float* weight, int32_t K, int32_t Cout,
+                                const uint16_t* seg, const uint32_t* entries, int32_t TM,
+                                float* out, int64_t n_out,
+                                const insmos_epilogue_t* ep, void* stream);
+
 /* Tensor-core path of the same convolution (3xTF32 on mma.sync m16n8k8, fp32 accumulate, fp32-accurate).
  * The weights are first rearranged ONCE per layer into tensor-core fragment order, pre-split into TF32 hi/lo
  * (wfrag: insmos_conv_wfrag_elems(K,Cin,Cout) 32-bit words, 16-byte aligned); the convolution then takes wfrag. */

@@ -277,6 +277,12 @@ def _epilogue(scale=None, shift=None, bias=None, residual=None, relu=False):
     return ep, keep
 
 
+import os as _os
+
+# sparse-conv algorithm used when algo=0: 1 = exact fp32 FFMA (thread per pair), 2 = tensor cores (3xTF32 mma.sync),
+# 3 = first-generation SIMT kernel (any shape).  INSMOS_CONV_ALGO overrides for A/B measurements.
+DEFAULT_CONV_ALGO = int(_os.environ.get("INSMOS_CONV_ALGO", "1"))
+
 _WFRAG_CACHE = {}
 
 
@@ -307,12 +313,17 @@ def sparse_conv(feat, weight, rb, scale=None, shift=None, bias=None, residual=No
                          % (tuple(feat.shape), tuple(weight.shape), rb.K, rb.n_in))
     out = torch.empty((rb.n_out, Cout), dtype=F32, device=feat.device)
     ep, keep = _epilogue(scale, shift, bias, residual, relu)
-    wf = prepared_weights(weight) if algo != 1 else None
+    if algo == 0:
+        algo = DEFAULT_CONV_ALGO if Cout % 4 == 0 else 2
+    wf = prepared_weights(weight) if algo == 2 else None
     if _lib.PROFILE is not None:          # algorithmic bytes / flops of this launch (SURVEY 8d formula)
         P = rb.num_pairs
         _lib.NEXT_META = {"bytes": 4 * (rb.n_in * Cin + rb.n_out * Cout) + 8 * P + 4 * K * Cin * Cout,
                           "flops": 2 * P * Cin * Cout, "pairs": P, "K": K, "Cin": Cin, "Cout": Cout, "n_out": rb.n_out}
     if algo == 1:
+        call("insmos_sparse_conv_fwd_ffma", _p(feat), rb.n_in, Cin, _p(weight), K, Cout, _p(rb.seg), _p(rb.entries), rb.TM,
+             _p(out), rb.n_out, C.byref(ep), _stream())
+    elif algo == 3:
         call("insmos_sparse_conv_fwd", _p(feat), rb.n_in, Cin, _p(weight), K, Cout, _p(rb.seg), _p(rb.entries), rb.TM,
              _p(out), rb.n_out, C.byref(ep), 1, _stream())
     else:

@@ -22,7 +22,7 @@ def _setup(cuda, ksize, seed=7):
     return cs, c, maps, rb
 
 
-@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("algo", [1, 2, 3])
 @pytest.mark.parametrize("Cin,Cout", [(1, 8), (8, 8), (16, 8), (24, 16), (48, 32), (7, 16), (19, 16), (131, 128), (64, 64)])
 def test_sparse_conv_matches_oracle(cuda, algo, Cin, Cout):
     cs, c, maps, rb = _setup(cuda, [3, 3, 3, 3])
@@ -35,7 +35,7 @@ def test_sparse_conv_matches_oracle(cuda, algo, Cin, Cout):
     assert torch.allclose(out, ref, rtol=RTOL, atol=ATOL), "max abs err %.3e (ref max %.3f)" % (err, ref.abs().max())
 
 
-@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("algo", [1, 2, 3])
 @pytest.mark.parametrize("TM", [16, 32, 64, 128])
 def test_sparse_conv_tile_sizes_and_epilogue(cuda, algo, TM):
     cs, c, maps, _ = _setup(cuda, [3, 3, 3, 3])
@@ -58,7 +58,7 @@ def test_conv0_125_offsets_single_channel(cuda):
     feats = torch.full((len(c), 1), 0.5)
     W = torch.randn((125, 1, 8), generator=g)
     ref = me.conv(feats, W, maps, len(c))
-    for algo in (0, 1, 2):
+    for algo in (0, 1, 2, 3):
         out = ops.sparse_conv(feats.to(cuda), W.to(cuda), rb, algo=algo).cpu()
         assert torch.allclose(out, ref, rtol=RTOL, atol=ATOL)
 
@@ -73,12 +73,12 @@ def test_strided_and_transposed_conv(cuda):
     W = torch.randn((8, 8, 16), generator=g) / 4.0
     rb = ops.build_rulebook(cg, cs, ops.spec_me_cube([2, 2, 2, 1], [1, 1, 1, 1]))
     ref = me.conv(feats, W, maps, len(co))
-    for algo in (1, 2):
+    for algo in (1, 2, 3):
         assert torch.allclose(ops.sparse_conv(feats.to(cuda), W.to(cuda), rb, algo=algo).cpu(), ref, rtol=RTOL, atol=ATOL)
     Wt = torch.randn((8, 16, 8), generator=g) / 4.0
     rbt = ops.build_rulebook(cs, cg, ops.spec_me_up([2, 2, 2, 1], [2, 2, 2, 1], [1, 1, 1, 1]))
     reft = me.conv(ref, Wt, me.transpose_map(maps), len(c))
-    for algo in (1, 2):
+    for algo in (1, 2, 3):
         assert torch.allclose(ops.sparse_conv(ref.to(cuda), Wt.to(cuda), rbt, algo=algo).cpu(), reft, rtol=RTOL, atol=ATOL)
 
 

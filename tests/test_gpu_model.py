@@ -154,14 +154,14 @@ def test_fresh_input_matches_oracle_graph(cuda):
 
 
 def test_sparse_conv_algorithms_agree_in_model(cuda):
-    """same forward with the SIMT fp32 kernels forced == tensor-core 3xTF32 path within 1e-3"""
+    """same forward with the tensor-core 3xTF32 kernels forced == default exact-fp32 FFMA path within 1e-3"""
     meta, shapes, sd, pts, gold = golden_util.load("small_nodet")
     net = _net(cuda, sd)
     from insmos_b200 import ops
     _, _, logits_auto = _run(net, pts, cuda)
     orig = ops.sparse_conv
     try:
-        ops.sparse_conv = lambda *a, **k: orig(*a, **{**k, "algo": 1})
+        ops.sparse_conv = lambda *a, **k: orig(*a, **{**k, "algo": 2})
         _, _, logits_simt = _run(net, pts, cuda)
     finally:
         ops.sparse_conv = orig
