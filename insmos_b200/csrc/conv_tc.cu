@@ -155,30 +155,40 @@ k_spconv_tc3(TcArgs p) {
             const float* x_lo = in + (size_t)(ce_lo & INSMOS_ROW_MASK) * Cin;
             const float* x_hi = in + (size_t)(ce_hi & INSMOS_ROW_MASK) * Cin;
             const uint4* wk = p.wf + ((int64_t)kc * p.NT8 + nt0) * KS * 32 + lane;
-#pragma unroll 4
-            for (int ks = 0; ks < KS; ++ks) {
-                const int col = ks * 8 + 2 * t;
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // (g,2t) (g+8,2t) (g,2t+1) (g+8,2t+1)
-                if (even) {
-                    if (col < Cin) {
-                        if (cv_lo) { const float2 v = __ldg(reinterpret_cast<const float2*>(x_lo + col)); a0 = v.x; a2 = v.y; }
-                        if (cv_hi) { const float2 v = __ldg(reinterpret_cast<const float2*>(x_hi + col)); a1 = v.x; a3 = v.y; }
+            constexpr int KG = 8;                            // k-steps whose loads are all in flight together
+            for (int ks0 = 0; ks0 < KS; ks0 += KG) {
+                float2 rl[KG], rh[KG];
+                uint4 b[KG][NT];
+#pragma unroll
+                for (int u = 0; u < KG; ++u) {
+                    const int col = (ks0 + u) * 8 + 2 * t;
+                    rl[u] = make_float2(0.f, 0.f); rh[u] = make_float2(0.f, 0.f);
+                    if (even) {
+                        if (col < Cin) {
+                            if (cv_lo) rl[u] = __ldg(reinterpret_cast<const float2*>(x_lo + col));
+                            if (cv_hi) rh[u] = __ldg(reinterpret_cast<const float2*>(x_hi + col));
+                        }
+                    } else {
+                        if (col < Cin) { if (cv_lo) rl[u].x = __ldg(x_lo + col); if (cv_hi) rh[u].x = __ldg(x_hi + col); }
+                        if (col + 1 < Cin) { if (cv_lo) rl[u].y = __ldg(x_lo + col + 1); if (cv_hi) rh[u].y = __ldg(x_hi + col + 1); }
                     }
-                } else {
-                    if (col < Cin) { if (cv_lo) a0 = __ldg(x_lo + col); if (cv_hi) a1 = __ldg(x_hi + col); }
-                    if (col + 1 < Cin) { if (cv_lo) a2 = __ldg(x_lo + col + 1); if (cv_hi) a3 = __ldg(x_hi + col + 1); }
+#pragma unroll
+                    for (int j = 0; j < NT; ++j)
+                        b[u][j] = (ks0 + u < KS) ? __ldg(wk + ((int64_t)j * KS + ks0 + u) * 32) : make_uint4(0u, 0u, 0u, 0u);
                 }
-                uint4 b[NT];
 #pragma unroll
-                for (int j = 0; j < NT; ++j) b[j] = __ldg(wk + ((int64_t)j * KS + ks) * 32);
-                uint32_t ah[4], al[4];
-                split_trunc(a0, ah[0], al[0]); split_trunc(a1, ah[1], al[1]);
-                split_trunc(a2, ah[2], al[2]); split_trunc(a3, ah[3], al[3]);
+                for (int u = 0; u < KG; ++u) {
+                    if (ks0 + u < KS) {
+                        uint32_t ah[4], al[4];
+                        split_trunc(rl[u].x, ah[0], al[0]); split_trunc(rh[u].x, ah[1], al[1]);
+                        split_trunc(rl[u].y, ah[2], al[2]); split_trunc(rh[u].y, ah[3], al[3]);
 #pragma unroll
-                for (int j = 0; j < NT; ++j) {
-                    mma_tf32x(d[j], al, b[j].x, b[j].y);
-                    mma_tf32x(d[j], ah, b[j].z, b[j].w);
-                    mma_tf32x(d[j], ah, b[j].x, b[j].y);
+                        for (int j = 0; j < NT; ++j) {
+                            mma_tf32x(d[j], al, b[u][j].x, b[u][j].y);
+                            mma_tf32x(d[j], ah, b[u][j].z, b[u][j].w);
+                            mma_tf32x(d[j], ah, b[u][j].x, b[u][j].y);
+                        }
+                    }
                 }
             }
         }
@@ -219,7 +229,7 @@ k_spconv_tc3(TcArgs p) {
 // accumulator needs no atomics; a block barrier separates buckets.
 #define BIG_WARPS 8
 template <int NT>
-__global__ void __launch_bounds__(BIG_WARPS * 32)
+__global__ void __launch_bounds__(BIG_WARPS * 32, 2)
 k_spconv_tc_big(TcArgs p, int G, int n_slices) {
     constexpr int CN = NT * 8;
     extern __shared__ __align__(16) float sm[];
@@ -264,28 +274,40 @@ k_spconv_tc_big(TcArgs p, int G, int n_slices) {
                 float d[NT][4];
 #pragma unroll
                 for (int j = 0; j < NT; ++j) { d[j][0] = d[j][1] = d[j][2] = d[j][3] = 0.0f; }
-#pragma unroll 4
-                for (int ks = 0; ks < KS; ++ks) {
-                    const int col = ks * 8 + 2 * t;
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                    if (even) {
-                        if (col < Cin) {
-                            if (v_lo) { const float2 v = __ldg(reinterpret_cast<const float2*>(x_lo + col)); a0 = v.x; a2 = v.y; }
-                            if (v_hi) { const float2 v = __ldg(reinterpret_cast<const float2*>(x_hi + col)); a1 = v.x; a3 = v.y; }
-                        }
-                    } else {
-                        if (col < Cin) { if (v_lo) a0 = __ldg(x_lo + col); if (v_hi) a1 = __ldg(x_hi + col); }
-                        if (col + 1 < Cin) { if (v_lo) a2 = __ldg(x_lo + col + 1); if (v_hi) a3 = __ldg(x_hi + col + 1); }
-                    }
-                    uint32_t ah[4], al[4];
-                    split_trunc(a0, ah[0], al[0]); split_trunc(a1, ah[1], al[1]);
-                    split_trunc(a2, ah[2], al[2]); split_trunc(a3, ah[3], al[3]);
+                // k-steps in groups of KG: ALL gathered-row loads of a group are issued before the first is consumed,
+                // so a chunk pays ~one L2 round trip per group instead of one per k-step
+                constexpr int KG = 16;
+                for (int ks0 = 0; ks0 < KS; ks0 += KG) {
+                    float2 rl[KG], rh[KG];
 #pragma unroll
-                    for (int j = 0; j < NT; ++j) {
-                        const uint4 b = wbuf[(j * KS + ks) * 32 + lane];
-                        mma_tf32x(d[j], al, b.x, b.y);
-                        mma_tf32x(d[j], ah, b.z, b.w);
-                        mma_tf32x(d[j], ah, b.x, b.y);
+                    for (int u = 0; u < KG; ++u) {
+                        const int col = (ks0 + u) * 8 + 2 * t;
+                        rl[u] = make_float2(0.f, 0.f); rh[u] = make_float2(0.f, 0.f);
+                        if (even) {
+                            if (col < Cin) {
+                                if (v_lo) rl[u] = __ldg(reinterpret_cast<const float2*>(x_lo + col));
+                                if (v_hi) rh[u] = __ldg(reinterpret_cast<const float2*>(x_hi + col));
+                            }
+                        } else {
+                            if (col < Cin) { if (v_lo) rl[u].x = __ldg(x_lo + col); if (v_hi) rh[u].x = __ldg(x_hi + col); }
+                            if (col + 1 < Cin) { if (v_lo) rl[u].y = __ldg(x_lo + col + 1); if (v_hi) rh[u].y = __ldg(x_hi + col + 1); }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < KG; ++u) {
+                        const int ks = ks0 + u;
+                        if (ks < KS) {
+                            uint32_t ah[4], al[4];
+                            split_trunc(rl[u].x, ah[0], al[0]); split_trunc(rh[u].x, ah[1], al[1]);
+                            split_trunc(rl[u].y, ah[2], al[2]); split_trunc(rh[u].y, ah[3], al[3]);
+#pragma unroll
+                            for (int j = 0; j < NT; ++j) {
+                                const uint4 b = wbuf[(j * KS + ks) * 32 + lane];
+                                mma_tf32x(d[j], al, b.x, b.y);
+                                mma_tf32x(d[j], ah, b.z, b.w);
+                                mma_tf32x(d[j], ah, b.x, b.y);
+                            }
+                        }
                     }
                 }
                 const int r_lo = (gi * TM + (int)(e_lo >> INSMOS_ROW_BITS)) * CN + 2 * t;
@@ -375,8 +397,10 @@ extern "C" int insmos_sparse_conv_fwd_tc(const float* in, int64_t n_in, int32_t 
     if (a.ep.scale && !a.ep.shift) return INSMOS_ERR_INVALID_ARG;
     if (n_out == 0) return INSMOS_OK;
     a.groups = a.NT8;
-    // >= 32 output channels: weight traffic dominates -> block-cooperative kernel with the slice's weights in smem
-    if (a.NT8 >= 4 && getenv("INSMOS_NO_BIG") == nullptr) return launch_tc_big(a, (cudaStream_t)stream);
+    // >= 64 output channels: weight traffic dominates -> block-cooperative kernel with the slice's weights in smem
+    // (measured on B200, C2 workload: 128->128 K=27 430 -> 283 us, 256->128 843 -> 494 us; at 32 channels the
+    // per-bucket barriers cost more than the saved traffic: 48->32 K=81 240 -> 550 us)
+    if (a.NT8 >= 8 && getenv("INSMOS_NO_BIG") == nullptr) return launch_tc_big(a, (cudaStream_t)stream);
     // two n-tiles per warp halve the redundant gathers; only when that still leaves thousands of warps
     if (a.NT8 % 2 == 0 && a.n_tiles * (a.NT8 / 2) >= 4096) {
         a.groups = a.NT8 / 2;

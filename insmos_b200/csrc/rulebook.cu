@@ -67,6 +67,7 @@ k_rulebook_tiles(const int32_t* __restrict__ out_coords, int64_t n_out,
             kd[k * 4 + d] = (d < ndim && spec.mode == 0) ? spec.b[d] + term[d] : term[d];
         }
         delta[k] = packed_delta(term[0], term[1], term[2], term[3]);
+        hist[k] = 0;
     }
     __syncthreads();
     if (fast) {                                                  // base key of every row: pack(c*a + b)
@@ -126,19 +127,8 @@ k_rulebook_tiles(const int32_t* __restrict__ out_coords, int64_t n_out,
                 }
             }
             nbr[r * K + k] = res;
+            if (res >= 0) atomicAdd(&hist[k], 1);               // bucket sizes (shared-memory integer atomics are native)
         }
-    }
-    __syncthreads();
-
-    // ---- phase B: bucket sizes (one warp per offset)
-    for (int k = warp; k < K; k += nwarps) {
-        int cnt = 0;
-        for (int r0 = 0; r0 < TM; r0 += 32) {
-            const int r = r0 + lane;
-            const bool hit = (r < TM) && nbr[r * K + k] >= 0;
-            cnt += __popc(__ballot_sync(0xffffffffu, hit));
-        }
-        if (lane == 0) hist[k] = cnt;
     }
     __syncthreads();
     if (warp == 0) {                                  // exclusive scan of hist[0..K) -> hist, hist[K] = total

@@ -281,7 +281,7 @@ import os as _os
 
 # sparse-conv algorithm used when algo=0: 1 = exact fp32 FFMA (thread per pair), 2 = tensor cores (3xTF32 mma.sync),
 # 3 = first-generation SIMT kernel (any shape).  INSMOS_CONV_ALGO overrides for A/B measurements.
-DEFAULT_CONV_ALGO = int(_os.environ.get("INSMOS_CONV_ALGO", "1"))
+DEFAULT_CONV_ALGO = int(_os.environ.get("INSMOS_CONV_ALGO", "2"))     # measured fastest on B200 in round 1
 
 _WFRAG_CACHE = {}
 
