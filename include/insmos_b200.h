@@ -229,6 +229,15 @@ int insmos_conv2d_nhwc_tc(const float* in, int32_t H, int32_t W, int32_t Cin,
                           const float* weight, int32_t mode, int32_t Cout,
                           const float* bias, int32_t relu, float* out, void* stream);
 
+/* Same convolution on the 5th-generation tensor cores: tcgen05.mma kind::tf32 (3xTF32 split), accumulators in TMEM,
+ * weight tiles by TMA bulk copy, mbarrier pipeline (bev_tcgen05.cu).  The weights are first rearranged once per layer
+ * into pre-swizzled TF32 hi/lo tile images (wimg: insmos_bev_wimg_elems(...) floats). */
+int64_t insmos_bev_wimg_elems(int32_t taps, int32_t Cin, int32_t Cout);
+int insmos_bev_prep_weights_tcgen05(const float* weight, int32_t taps, int32_t Cin, int32_t Cout, float* wimg, void* stream);
+int insmos_conv2d_nhwc_tcgen05(const float* in, int32_t H, int32_t W, int32_t Cin,
+                               const float* wimg, int32_t mode, int32_t Cout,
+                               const float* bias, int32_t relu, float* out, void* stream);
+
 /* SparseConvTensor.dense() + HeightCompression view, channels-last: out[(y*W+x), c*D+z] (height_compression.py:26-30) */
 int insmos_dense_scatter_nhwc(const float* feat, const int32_t* coords, int64_t n, int32_t C,
                               int32_t D, int32_t H, int32_t W, float* out, void* stream);

@@ -156,6 +156,24 @@ k_spconv_tc3(TcArgs p) {
             const float* x_hi = in + (size_t)(ce_hi & INSMOS_ROW_MASK) * Cin;
             const uint4* wk = p.wf + ((int64_t)kc * p.NT8 + nt0) * KS * 32 + lane;
             constexpr int KG = 8;                            // k-steps whose loads are all in flight together
+            if (KS <= 3) {                                   // few k-steps: the plain loop (no group overhead)
+                for (int ks = 0; ks < KS; ++ks) {
+                    const int col = ks * 8 + 2 * t;
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                    if (col < Cin) { if (cv_lo) a0 = __ldg(x_lo + col); if (cv_hi) a1 = __ldg(x_hi + col); }
+                    if (col + 1 < Cin) { if (cv_lo) a2 = __ldg(x_lo + col + 1); if (cv_hi) a3 = __ldg(x_hi + col + 1); }
+                    uint32_t ah[4], al[4];
+                    split_trunc(a0, ah[0], al[0]); split_trunc(a1, ah[1], al[1]);
+                    split_trunc(a2, ah[2], al[2]); split_trunc(a3, ah[3], al[3]);
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        const uint4 b = __ldg(wk + ((int64_t)j * KS + ks) * 32);
+                        mma_tf32x(d[j], al, b.x, b.y);
+                        mma_tf32x(d[j], ah, b.z, b.w);
+                        mma_tf32x(d[j], ah, b.x, b.y);
+                    }
+                }
+            } else
             for (int ks0 = 0; ks0 < KS; ks0 += KG) {
                 float2 rl[KG], rh[KG];
                 uint4 b[KG][NT];

@@ -315,6 +315,8 @@ def sparse_conv(feat, weight, rb, scale=None, shift=None, bias=None, residual=No
     ep, keep = _epilogue(scale, shift, bias, residual, relu)
     if algo == 0:
         algo = DEFAULT_CONV_ALGO if Cout % 4 == 0 else 2
+        if algo == 2 and Cin < 8 and Cout % 4 == 0 and Cout <= 16:
+            algo = 1          # 1..7 input channels: a tensor-core k-step would be mostly padding; fp32 thread-per-pair
     wf = prepared_weights(weight) if algo == 2 else None
     if _lib.PROFILE is not None:          # algorithmic bytes / flops of this launch (SURVEY 8d formula)
         P = rb.num_pairs
@@ -436,7 +438,27 @@ def center_decode(cls, box, out_size_factor, vx, vy, x_min, y_min, hw=None):
     return boxes, scores, labels
 
 
-def conv2d_nhwc(x, H, W, weight, mode, bias=None, relu=False):
+# dense BEV conv implementation: "tcgen05" (UTCHMMA + TMEM + TMA, bev_tcgen05.cu) or "mma" (mma.sync, bev.cu)
+BEV_IMPL = _os.environ.get("INSMOS_BEV_IMPL", "mma")
+_WIMG_CACHE = {}
+
+
+def bev_weight_images(weight):
+    """pre-swizzled TF32 hi/lo tile images of a [taps,Cin,Cout] weight for the tcgen05 kernel (cached)."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device.index)
+    hit = _WIMG_CACHE.get(key)
+    if hit is not None:
+        return hit[0]
+    taps, Cin, Cout = weight.shape
+    img = torch.empty(_lib.load().insmos_bev_wimg_elems(taps, Cin, Cout), dtype=F32, device=weight.device)
+    call("insmos_bev_prep_weights_tcgen05", _p(weight), taps, Cin, Cout, _p(img), _stream())
+    if len(_WIMG_CACHE) > 64:
+        _WIMG_CACHE.clear()
+    _WIMG_CACHE[key] = (img, weight)
+    return img
+
+
+def conv2d_nhwc(x, H, W, weight, mode, bias=None, relu=False, impl=None):
     """dense conv on tensor cores (3xTF32): x [H*W,Cin] channels-last, weight [taps,Cin,Cout] (BN folded).
     mode 0: 3x3 pad 1; 1: 1x1; 2: 2x2 stride-2 transposed conv (output [2H*2W,Cout])."""
     x = _req(x, F32, "conv2d_nhwc")
@@ -446,7 +468,11 @@ def conv2d_nhwc(x, H, W, weight, mode, bias=None, relu=False):
     out = torch.empty(((4 if mode == 2 else 1) * H * W, Cout), dtype=F32, device=x.device)
     if bias is not None:
         bias = _req(bias, F32, "conv2d_nhwc")
-    call("insmos_conv2d_nhwc_tc", _p(x), H, W, Cin, _p(weight), mode, Cout, _p(bias), 1 if relu else 0, _p(out), _stream())
+    if (impl or BEV_IMPL) == "tcgen05":
+        img = bev_weight_images(weight)
+        call("insmos_conv2d_nhwc_tcgen05", _p(x), H, W, Cin, _p(img), mode, Cout, _p(bias), 1 if relu else 0, _p(out), _stream())
+    else:
+        call("insmos_conv2d_nhwc_tc", _p(x), H, W, Cin, _p(weight), mode, Cout, _p(bias), 1 if relu else 0, _p(out), _stream())
     return out
 
 

@@ -18,20 +18,22 @@ def _nhwc(x):                      # [1,C,H,W] -> [H*W, C]
     return x[0].permute(1, 2, 0).reshape(-1, x.shape[1]).contiguous()
 
 
+@pytest.mark.parametrize("impl", ["mma", "tcgen05"])
 @pytest.mark.parametrize("Cin,Cout,H,W", [(256, 128, 125, 150), (128, 128, 125, 150), (32, 128, 7, 9)])
-def test_conv3x3_matches_torch(cuda, Cin, Cout, H, W):
+def test_conv3x3_matches_torch(cuda, Cin, Cout, H, W, impl):
     g = torch.Generator().manual_seed(Cin + H)
     x = torch.randn((1, Cin, H, W), generator=g)
     w = torch.randn((Cout, Cin, 3, 3), generator=g) / np.sqrt(9 * Cin)
     b = torch.randn(Cout, generator=g)
     ref = torch.relu(F.conv2d(x, w, b, padding=1))
     wk = w.permute(2, 3, 1, 0).reshape(9, Cin, Cout).contiguous()
-    out = ops.conv2d_nhwc(_nhwc(x).to(cuda), H, W, wk.to(cuda), 0, bias=b.to(cuda), relu=True).cpu()
+    out = ops.conv2d_nhwc(_nhwc(x).to(cuda), H, W, wk.to(cuda), 0, bias=b.to(cuda), relu=True, impl=impl).cpu()
     err = (out - _nhwc(ref)).abs().max().item()
     assert err < TOL * max(1.0, ref.abs().max().item()), err
 
 
-def test_deconv2x2_and_1x1_match_torch(cuda):
+@pytest.mark.parametrize("impl", ["mma", "tcgen05"])
+def test_deconv2x2_and_1x1_match_torch(cuda, impl):
     g = torch.Generator().manual_seed(3)
     H, W, Cin, Cout = 125, 150, 128, 256
     x = torch.randn((1, Cin, H, W), generator=g)
@@ -39,12 +41,12 @@ def test_deconv2x2_and_1x1_match_torch(cuda):
     b = torch.randn(Cout, generator=g)
     ref = torch.relu(F.conv_transpose2d(x, w, b, stride=2))                     # [1,Cout,2H,2W]
     wk = w.permute(2, 3, 0, 1).reshape(4, Cin, Cout).contiguous()
-    out = ops.conv2d_nhwc(_nhwc(x).to(cuda), H, W, wk.to(cuda), 2, bias=b.to(cuda), relu=True).cpu()
+    out = ops.conv2d_nhwc(_nhwc(x).to(cuda), H, W, wk.to(cuda), 2, bias=b.to(cuda), relu=True, impl=impl).cpu()
     assert out.shape == (4 * H * W, Cout)
     assert (out - _nhwc(ref)).abs().max().item() < TOL * max(1.0, ref.abs().max().item())
     w1 = torch.randn((128, Cin, 1, 1), generator=g) / np.sqrt(Cin)
     ref1 = F.conv2d(x, w1)
-    out1 = ops.conv2d_nhwc(_nhwc(x).to(cuda), H, W, w1.flatten(1).t().reshape(1, Cin, 128).contiguous().to(cuda), 1).cpu()
+    out1 = ops.conv2d_nhwc(_nhwc(x).to(cuda), H, W, w1.flatten(1).t().reshape(1, Cin, 128).contiguous().to(cuda), 1, impl=impl).cpu()
     assert (out1 - _nhwc(ref1)).abs().max().item() < TOL * max(1.0, ref1.abs().max().item())
 
 
