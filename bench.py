@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-launches", default=None, help="write the per-C-ABI-call profile of one step (JSON lines)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -250,6 +251,10 @@ def main():
     conv_launches = sorted(({"ms": round(t, 4), **{k: m[k] for k in ("K", "Cin", "Cout", "n_out", "pairs")},
                              "alg_GBps": round(m["bytes"] / (t * 1e-3) / 1e9, 1)}
                             for name, t, m in prof[len(prof) // 2:] if m and "Cin" in m), key=lambda d: -d["ms"])[:16]
+    if args.dump_launches and rank == 0:
+        with open(args.dump_launches, "w") as fh:
+            for name, t, m in prof[len(prof) // 2:]:
+                fh.write(json.dumps({"call": name, "ms": round(t, 4), **(m or {})}) + "\n")
     peak, peak_src = peaks()
     top = max((k for k in fam if fam[k]["bytes"] > 0), key=lambda k: fam[k]["ms"])
     ach = fam[top]["bytes"] / (fam[top]["ms"] * 1e-3) / 1e9

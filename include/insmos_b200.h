@@ -160,6 +160,14 @@ int insmos_rulebook_build(const int32_t* out_coords, int64_t n_out,
                           uint16_t* seg, uint32_t* entries, unsigned long long* pair_count,
                           int32_t* counters, void* stream);
 
+/* Transposed (MinkowskiConvolutionTranspose, kernel == stride) map built without hash probes: the only pair of fine row
+ * i is (offset of i inside its coarse cell, parent[i]) where parent is the inverse map insmos_unique_coords(q) returned
+ * when the coarse set was made (ME derives the same map by swapping the strided one: minkunet.py:96-125).  `spec` is the
+ * mode-1 spec of insmos_rulebook_build; identical output layout and ordering. */
+int insmos_rulebook_build_up(const int32_t* fine_coords, int64_t n_fine, const int32_t* parent,
+                             const insmos_mapspec_t* spec, int32_t TM,
+                             uint16_t* seg, uint32_t* entries, unsigned long long* pair_count, void* stream);
+
 /* ---- feature ops -------------------------------------------------------------------------- */
 
 /* sparse convolution forward over a tiled rule book (a3, a8, a12).
@@ -189,6 +197,19 @@ int insmos_sparse_conv_fwd_tc(const float* in, int64_t n_in, int32_t Cin,
                               const uint16_t* seg, const uint32_t* entries, int32_t TM,
                               float* out, int64_t n_out,
                               const insmos_epilogue_t* ep, void* stream);
+
+/* 5th-generation tensor-core path of the same convolution (tcgen05.mma kind::tf32 with TMEM accumulators, TMA bulk
+ * copies of the weight tiles; spconv_umma.cu), for the wide layers: spconv SubMConv3d / SparseConv3d /
+ * SparseInverseConv3d with Cout in {16,32,...,256} (reference call sites spconv_unet.py:120-208).  Output-stationary
+ * implicit GEMM over 128-row super-tiles, 3xTF32 (fp32-accurate).  The weights are first rearranged ONCE per layer into
+ * pre-swizzled TF32 hi/lo operand images (wimg: insmos_conv_wimg_elems(K,Cin,Cout) floats; 0 = shape unsupported). */
+int64_t insmos_conv_wimg_elems(int32_t K, int32_t Cin, int32_t Cout);
+int insmos_conv_prep_weights_umma(const float* weight, int32_t K, int32_t Cin, int32_t Cout, float* wimg, void* stream);
+int insmos_sparse_conv_fwd_umma(const float* in, int64_t n_in, int32_t Cin,
+                                const float* wimg, int32_t K, int32_t Cout,
+                                const uint16_t* seg, const uint32_t* entries, int32_t TM,
+                                float* out, int64_t n_out,
+                                const insmos_epilogue_t* ep, void* stream);
 
 /* out[n,Cout] = in[n,Cin] . weight[Cin,Cout] + epilogue (ME kernel_size==1 conv, nn.Linear) */
 int insmos_linear_fwd(const float* in, int64_t n, int32_t Cin, const float* weight, int32_t Cout,

@@ -48,6 +48,7 @@ PROTOTYPES = {
                                     _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "insmos_rulebook_entries_capacity": (_I64, [_I64, _I32, _I32]),
     "insmos_rulebook_build": (C.c_int, [_P, _I64, _P, _I64, C.POINTER(MapSpec), _I32, _P, _P, _P, _P, _P]),
+    "insmos_rulebook_build_up": (C.c_int, [_P, _I64, _P, C.POINTER(MapSpec), _I32, _P, _P, _P, _P]),
     "insmos_sparse_conv_fwd": (C.c_int, [_P, _I64, _I32, _P, _I32, _I32, _P, _P, _I32, _P, _I64,
                                          C.POINTER(Epilogue), _I32, _P]),
     "insmos_sparse_conv_fwd_ffma": (C.c_int, [_P, _I64, _I32, _P, _I32, _I32, _P, _P, _I32, _P, _I64,
@@ -56,6 +57,10 @@ PROTOTYPES = {
     "insmos_conv_prep_weights": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
     "insmos_sparse_conv_fwd_tc": (C.c_int, [_P, _I64, _I32, _P, _I32, _I32, _P, _P, _I32, _P, _I64,
                                             C.POINTER(Epilogue), _P]),
+    "insmos_conv_wimg_elems": (_I64, [_I32, _I32, _I32]),
+    "insmos_conv_prep_weights_umma": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
+    "insmos_sparse_conv_fwd_umma": (C.c_int, [_P, _I64, _I32, _P, _I32, _I32, _P, _P, _I32, _P, _I64,
+                                              C.POINTER(Epilogue), _P]),
     "insmos_linear_fwd": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, C.POINTER(Epilogue), _P]),
     "insmos_affine_act": (C.c_int, [_P, _I64, _I32, _P, C.POINTER(Epilogue), _P]),
     "insmos_concat2": (C.c_int, [_P, _I32, _P, _I32, _I64, _P, _P]),

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libinsmos_b200.so")
-SOURCES = ["coords.cu", "rulebook.cu", "conv.cu", "conv_tc.cu", "conv_ffma.cu", "detect.cu", "bev.cu", "bev_tcgen05.cu"]
+SOURCES = ["coords.cu", "rulebook.cu", "conv.cu", "conv_tc.cu", "conv_ffma.cu", "detect.cu", "bev.cu", "bev_tcgen05.cu", "spconv_umma.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -34,7 +34,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"),
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "umma.cuh"),
                                                        os.path.join(HERE, "..", "include", "insmos_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 

@@ -38,12 +38,14 @@ class CoordinateManager:
         self.D = D
         self.sets = {}          # tensor_stride tuple -> ops.CoordSet
         self.rulebooks = {}
+        self.parents = {}       # (fine key, coarse key) -> int32 [n_fine] row of each fine voxel's coarse cell
 
     def stride(self, key, stride):
         new_key = tuple(k * s for k, s in zip(key, stride))
         if new_key not in self.sets:
-            cs, _ = ops.unique_coords(self.sets[key].coords, q=list(new_key))
+            cs, parent = ops.unique_coords(self.sets[key].coords, q=list(new_key))
             self.sets[new_key] = cs
+            self.parents[(key, new_key)] = parent
         return new_key
 
     def rulebook(self, kind, in_key, out_key, ksize, stride):
@@ -54,7 +56,9 @@ class CoordinateManager:
                 spec = ops.spec_me_cube(list(ksize), list(in_key))
             else:
                 spec = ops.spec_me_up(list(ksize), list(stride), list(out_key))
-            rb = ops.build_rulebook(self.sets[out_key], self.sets[in_key], spec)
+            # transposed map: the coarse set was made from the fine one, so every fine row already knows its parent
+            parent = self.parents.get((out_key, in_key)) if kind == "up" else None
+            rb = ops.build_rulebook(self.sets[out_key], self.sets[in_key], spec, parent=parent)
             self.rulebooks[k] = rb
         return rb
 

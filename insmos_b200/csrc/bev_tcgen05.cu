@@ -16,7 +16,7 @@
 // Descriptor encodings follow cute/arch/mma_sm100_desc.hpp / cute/atom/mma_traits_sm100.hpp (vendored CUTLASS headers):
 // K-major SWIZZLE_128B: LBO = 1, SBO = 64 (1024 B between 8-row groups), version = 1, layout_type = 2; the K-step
 // inside the 128-byte row advances the start address by 32 bytes.
-#include "common.cuh"
+#include "umma.cuh"
 
 #define T5_BM 128
 #define T5_BN 128
@@ -25,53 +25,6 @@
 #define T5_TILE_BYTES (T5_BM * 128)                 // one 128x32 fp32 operand image
 #define T5_STAGE_BYTES (4 * T5_TILE_BYTES)          // A_hi, A_lo, B_hi, B_lo
 #define T5_THREADS 192
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
-    // start address (>>4) | LBO=1 (<<16) | SBO=64 (<<32) | version=1 (bit 46) | layout SWIZZLE_128B=2 (bits 61-63)
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void split_rn(float x, float& hi, float& lo) {
-    const uint32_t h = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;     // round-to-nearest TF32 (unbiased)
-    hi = __uint_as_float(h);
-    lo = x - hi;                                                          // exact; tensor core ignores its low 13 bits
-}
 
 struct T5Args {
     const float* in;      // [H*W, Cin] NHWC

@@ -41,16 +41,17 @@ __device__ __forceinline__ void mma_tf32x(float (&d)[4], const uint32_t (&a)[4],
 struct TcArgs {
     const float* in; const uint4* wf; const uint16_t* seg; const uint32_t* entries; float* out;
     int64_t n_out, n_tiles; int groups, Cin, Cout, K, TM, KS, NT8;
+    int wpt;                                                 // warps sharing one (tile, channel group): bucket k goes to warp k % wpt
     insmos_epilogue_t ep;
 };
 
 // chunk iterator over the non-empty buckets of one tile
 struct ChunkIt {
-    const int* sseg; int K, k, s0, n, c0;
+    const int* sseg; int K, k, s0, n, c0, kstep;
     __device__ __forceinline__ bool next() {
         c0 += 16;
         while (c0 >= n) {
-            if (++k >= K) return false;
+            if ((k += kstep) >= K) return false;
             s0 = sseg[k]; n = sseg[k + 1] - s0; c0 = 0;
         }
         return true;
@@ -58,23 +59,29 @@ struct ChunkIt {
 };
 
 template <int NT, int KSC>
-__global__ void __launch_bounds__(TC_WARPS * 32)
+__global__ void __launch_bounds__(256)
 k_spconv_tc3(TcArgs p) {
     constexpr int CW = NT * 8;
     constexpr int KSR = KSC > 0 ? KSC : 1;
     extern __shared__ __align__(16) float sm[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int64_t wglobal = (int64_t)blockIdx.x * TC_WARPS + warp;
-    const int64_t tile = wglobal / p.groups;
-    const int grp = (int)(wglobal - tile * p.groups);
-    if (tile >= p.n_tiles) return;                           // warps are independent: no block barrier below
+    // a UNIT = (tile of TM output rows, group of NT n-tiles) is shared by wpt warps: warp `sub` of the unit takes the
+    // buckets k = sub, sub + wpt, ... into a private copy of the accumulator tile; the copies are summed in the
+    // epilogue.  Large tiles keep the 16-pair chunks full (a bucket of a TM-row tile holds ~0.2*TM pairs in the 4D
+    // maps), several warps per tile keep the SMs occupied (ncu of v3: 24 % warps active with one warp per tile).
+    const int wpt = p.wpt;
+    const int unit_local = warp / wpt, sub = warp - unit_local * wpt;
+    const int64_t unit = (int64_t)blockIdx.x * (nwarps / wpt) + unit_local;
+    const int64_t tile = unit / p.groups;
+    const int grp = (int)(unit - tile * p.groups);
+    const bool active = tile < p.n_tiles;
     const int TM = p.TM, K = p.K;
     const int Cin = KSC > 0 ? KSC * 8 : p.Cin;
     const int KS = KSC > 0 ? KSC : p.KS;
     float* acc = sm + (size_t)warp * TM * CW;
-    int* sseg = reinterpret_cast<int*>(sm + (size_t)TC_WARPS * TM * CW) + warp * (K + 1);
-    {
+    int* sseg = reinterpret_cast<int*>(sm + (size_t)nwarps * TM * CW) + warp * (K + 1);
+    if (active) {
         const uint16_t* tseg = p.seg + tile * (K + 1);
         for (int k = lane; k <= K; k += 32) sseg[k] = tseg[k];
         for (int i = lane; i < TM * CW; i += 32) acc[i] = 0.0f;
@@ -87,10 +94,10 @@ k_spconv_tc3(TcArgs p) {
     // three-stage software pipeline over chunks: entries of chunk i+2 and gathered rows of chunk i+1 are in flight
     // while chunk i is multiplied, so neither global-load latency sits on the critical path.
     struct Ent { uint32_t lo, hi; int k; bool vlo, vhi, ok; };
-    ChunkIt it{sseg, K, -1, 0, 0, 0};
+    ChunkIt it{sseg, K, sub - wpt, 0, 0, 0, wpt};
     auto fetch = [&]() -> Ent {
         Ent e; e.lo = 0u; e.hi = 0u; e.vlo = false; e.vhi = false;
-        e.ok = it.next(); e.k = it.k;
+        e.ok = active && it.next(); e.k = it.k;
         if (e.ok) {
             e.vlo = (it.c0 + g) < it.n; e.vhi = (it.c0 + g + 8) < it.n;
             if (e.vlo) e.lo = __ldg(tent + it.s0 + it.c0 + g);
@@ -227,12 +234,17 @@ k_spconv_tc3(TcArgs p) {
         __syncwarp();
         E0 = E1; E1 = E2;
     }
+    __syncthreads();                                         // the unit's wpt partial tiles are complete
+    if (!active) return;
     const int64_t row0 = tile * TM;
     const int rows = (int)((p.n_out - row0) < TM ? (p.n_out - row0) : TM);
     const int cbase = nt0 * 8;
-    for (int i = lane; i < rows * CW; i += 32) {
+    const float* acc0 = sm + (size_t)(unit_local * wpt) * TM * CW;
+    for (int i = sub * 32 + lane; i < rows * CW; i += wpt * 32) {
         const int r = i / CW, c = cbase + (i % CW);
-        if (c < p.Cout) p.out[(row0 + r) * p.Cout + c] = tc_epilogue(acc[i], c, row0 + r, p.Cout, p.ep);
+        float v = acc0[i];
+        for (int w = 1; w < wpt; ++w) v += acc0[(size_t)w * TM * CW + i];
+        if (c < p.Cout) p.out[(row0 + r) * p.Cout + c] = tc_epilogue(v, c, row0 + r, p.Cout, p.ep);
     }
 }
 
@@ -368,16 +380,23 @@ static int launch_tc_big(const TcArgs& a, cudaStream_t st) {
 }
 
 template <int NT, int KSC>
-static int launch_tc3(const TcArgs& a, cudaStream_t st) {
-    const size_t smem = sizeof(float) * (size_t)TC_WARPS * a.TM * NT * 8 + sizeof(int) * (size_t)TC_WARPS * (a.K + 1);
+static int launch_tc3(TcArgs a, cudaStream_t st) {
+    // warps per unit: enough warps in flight to cover the gather latency on 148 SMs (~48 resident warps each)
+    const int64_t units = a.n_tiles * a.groups;
+    int wpt = 1;
+    while (wpt < 8 && units * wpt < 8192 && wpt * 2 <= a.K) wpt *= 2;
+    if (const char* e = getenv("INSMOS_WPT")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) wpt = v; }
+    while (wpt > 1 && sizeof(float) * (size_t)(wpt > 4 ? wpt : 4) * a.TM * NT * 8 > 96 * 1024) wpt /= 2;
+    a.wpt = wpt;
+    const int nwarps = wpt > TC_WARPS ? wpt : TC_WARPS;
+    const size_t smem = sizeof(float) * (size_t)nwarps * a.TM * NT * 8 + sizeof(int) * (size_t)nwarps * (a.K + 1);
     if (smem > 220 * 1024) return INSMOS_ERR_UNSUPPORTED;
     static thread_local size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_spconv_tc3<NT, KSC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const int64_t warps = a.n_tiles * a.groups;
-    k_spconv_tc3<NT, KSC><<<(unsigned)ceil_div64(warps, TC_WARPS), TC_WARPS * 32, smem, st>>>(a);
+    k_spconv_tc3<NT, KSC><<<(unsigned)ceil_div64(units, nwarps / wpt), nwarps * 32, smem, st>>>(a);
     INSMOS_CHECK_LAUNCH("k_spconv_tc3");
     return INSMOS_OK;
 }

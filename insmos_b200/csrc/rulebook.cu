@@ -38,7 +38,7 @@ k_rulebook_tiles(const int32_t* __restrict__ out_coords, int64_t n_out,
                  const insmos_slot_t* __restrict__ table, uint64_t mask,
                  insmos_mapspec_t spec, int TM,
                  uint16_t* __restrict__ seg, uint32_t* __restrict__ entries,
-                 unsigned long long* pair_count) {
+                 unsigned long long* pair_count, const int32_t* __restrict__ parent) {
     extern __shared__ __align__(16) int smem[];
     const int K = spec.K, ncol = spec.ncol, ndim = spec.ndim;
     int* nbr = smem;                                            // [TM*K] in-row or -1
@@ -122,7 +122,8 @@ k_rulebook_tiles(const int32_t* __restrict__ out_coords, int64_t n_out,
                                 ci[d] = b0;
                             }
                     }
-                    if (ok && coord_in_range(c[0], ci[0], ci[1], ci[2], ci[3]))
+                    if (ok && parent) res = __ldg(parent + row0 + r);        // transposed map: the one pair of a fine row is (k, its parent)
+                    else if (ok && coord_in_range(c[0], ci[0], ci[1], ci[2], ci[3]))
                         res = table_find_row(table, mask, pack_key(c[0], ci[0], ci[1], ci[2], ci[3]));
                 }
             }
@@ -165,13 +166,17 @@ k_rulebook_tiles(const int32_t* __restrict__ out_coords, int64_t n_out,
     }
 }
 
-extern "C" int insmos_rulebook_build(const int32_t* out_coords, int64_t n_out,
-                                     const insmos_slot_t* in_table, int64_t in_cap,
-                                     const insmos_mapspec_t* spec, int32_t TM,
-                                     uint16_t* seg, uint32_t* entries, unsigned long long* pair_count,
-                                     int32_t* counters, void* stream) {
-    (void)counters;
-    if (!out_coords || !in_table || !spec || !seg || !entries || n_out < 0) return INSMOS_ERR_INVALID_ARG;
+static int rulebook_build_impl(const int32_t* out_coords, int64_t n_out,
+                               const insmos_slot_t* in_table, int64_t in_cap, const int32_t* parent,
+                               const insmos_mapspec_t* spec, int32_t TM,
+                               uint16_t* seg, uint32_t* entries, unsigned long long* pair_count, void* stream) {
+    if (!out_coords || !spec || !seg || !entries || n_out < 0) return INSMOS_ERR_INVALID_ARG;
+    if (parent) {
+        if (spec->mode != 1) return INSMOS_ERR_INVALID_ARG;
+        in_cap = 1;                                                    // no table: every lookup is parent[row]
+    } else {
+        if (!in_table) return INSMOS_ERR_INVALID_ARG;
+    }
     if (in_cap <= 0 || (in_cap & (in_cap - 1))) return INSMOS_ERR_INVALID_ARG;
     if (TM != 16 && TM != 32 && TM != 64 && TM != 128) return INSMOS_ERR_INVALID_ARG;
     if (spec->K <= 0 || (int64_t)TM * spec->K >= 65536 || spec->ndim < 1 || spec->ndim > 4 ||
@@ -198,7 +203,26 @@ extern "C" int insmos_rulebook_build(const int32_t* out_coords, int64_t n_out,
     }
     const int64_t n_tiles = ceil_div64(n_out, TM);
     k_rulebook_tiles<<<(unsigned)n_tiles, RB_THREADS, smem, (cudaStream_t)stream>>>(
-        out_coords, n_out, in_table, (uint64_t)(in_cap - 1), *spec, TM, seg, entries, pair_count);
+        out_coords, n_out, in_table, (uint64_t)(in_cap - 1), *spec, TM, seg, entries, pair_count, parent);
     INSMOS_CHECK_LAUNCH("k_rulebook_tiles");
     return INSMOS_OK;
+}
+
+extern "C" int insmos_rulebook_build(const int32_t* out_coords, int64_t n_out,
+                                     const insmos_slot_t* in_table, int64_t in_cap,
+                                     const insmos_mapspec_t* spec, int32_t TM,
+                                     uint16_t* seg, uint32_t* entries, unsigned long long* pair_count,
+                                     int32_t* counters, void* stream) {
+    (void)counters;
+    return rulebook_build_impl(out_coords, n_out, in_table, in_cap, nullptr, spec, TM, seg, entries, pair_count, stream);
+}
+
+// Transposed (up-sampling) map without hash probes: a fine row's only pair is (offset of the row inside its coarse
+// cell, its parent row), and the parent row is the inverse map that insmos_unique_coords(q) returned when the coarse
+// coordinate set was made.  Same rule-book layout / ordering as insmos_rulebook_build with a mode-1 spec.
+extern "C" int insmos_rulebook_build_up(const int32_t* fine_coords, int64_t n_fine, const int32_t* parent,
+                                        const insmos_mapspec_t* spec, int32_t TM,
+                                        uint16_t* seg, uint32_t* entries, unsigned long long* pair_count, void* stream) {
+    if (!parent) return INSMOS_ERR_INVALID_ARG;
+    return rulebook_build_impl(fine_coords, n_fine, nullptr, 1, parent, spec, TM, seg, entries, pair_count, stream);
 }

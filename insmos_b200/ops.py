@@ -237,7 +237,10 @@ def choose_tile_rows(n_out, K):
     return tm
 
 
-def build_rulebook(out_set, in_set, spec, TM=None):
+def build_rulebook(out_set, in_set, spec, TM=None, parent=None):
+    """tiled rule book of the map in_set -> out_set.  parent (int32 [n_out], optional): for a transposed map (mode-1
+    spec) the row of every output (fine) row's coarse cell in in_set, as returned by unique_coords(q): the map is then
+    built without hash probes."""
     lib = _lib.load()
     K = int(spec.K)
     n_out = out_set.n
@@ -253,8 +256,15 @@ def build_rulebook(out_set, in_set, spec, TM=None):
     prof = _lib.PROFILE is not None
     if prof:
         _lib.NEXT_META = {"n_out": n_out, "K": K, "ncol": out_set.ncol}
-    call("insmos_rulebook_build", _p(out_set.coords), n_out, _p(in_set.table), in_set.cap, C.byref(spec), TM,
-         _p(seg), _p(entries), _p(pc), None, _stream())
+    if parent is not None:
+        parent = _req(parent, I32, "build_rulebook.parent")
+        if parent.shape[0] != n_out:
+            raise ValueError("build_rulebook: parent must have one entry per output row")
+        call("insmos_rulebook_build_up", _p(out_set.coords), n_out, _p(parent), C.byref(spec), TM,
+             _p(seg), _p(entries), _p(pc), _stream())
+    else:
+        call("insmos_rulebook_build", _p(out_set.coords), n_out, _p(in_set.table), in_set.cap, C.byref(spec), TM,
+             _p(seg), _p(entries), _p(pc), None, _stream())
     rb = Rulebook(seg, entries, TM, K, n_out, in_set.n, pc)
     if prof:                               # bytes_alg = coordinate rows read + 8 B per pair written
         _lib.PROFILE[-1][3]["bytes"] = 4 * out_set.ncol * n_out + 8 * rb.num_pairs
@@ -280,8 +290,37 @@ def _epilogue(scale=None, shift=None, bias=None, residual=None, relu=False):
 import os as _os
 
 # sparse-conv algorithm used when algo=0: 1 = exact fp32 FFMA (thread per pair), 2 = tensor cores (3xTF32 mma.sync),
-# 3 = first-generation SIMT kernel (any shape).  INSMOS_CONV_ALGO overrides for A/B measurements.
+# 3 = first-generation SIMT kernel (any shape), 4 = tcgen05/TMEM output-stationary implicit GEMM (wide layers).
+# INSMOS_CONV_ALGO overrides for A/B measurements.
 DEFAULT_CONV_ALGO = int(_os.environ.get("INSMOS_CONV_ALGO", "2"))     # measured fastest on B200 in round 1
+# wide layers (>= UMMA_MIN_C input AND output channels, K <= UMMA_MAX_K offsets) go to the tcgen05 kernel
+USE_UMMA = _os.environ.get("INSMOS_UMMA", "1") != "0"
+UMMA_MIN_CIN = int(_os.environ.get("INSMOS_UMMA_MIN_CIN", "32"))
+UMMA_MIN_COUT = int(_os.environ.get("INSMOS_UMMA_MIN_COUT", "32"))
+UMMA_MAX_K = int(_os.environ.get("INSMOS_UMMA_MAX_K", "32"))
+_WIMG_UMMA_CACHE = {}
+
+
+def umma_eligible(K, Cin, Cout):
+    return Cout % 16 == 0 and 16 <= Cout <= 256 and K <= 128 and (Cout <= 128 or Cout % 128 == 0)
+
+
+def prepared_weight_images(weight):
+    """pre-swizzled TF32 hi/lo operand images of a [K,Cin,Cout] weight for the tcgen05 sparse conv (cached)."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), weight.device.index)
+    hit = _WIMG_UMMA_CACHE.get(key)
+    if hit is not None:
+        return hit[0]
+    K, Cin, Cout = weight.shape
+    n = _lib.load().insmos_conv_wimg_elems(K, Cin, Cout)
+    if n <= 0:
+        raise ValueError("sparse_conv: shape K=%d Cin=%d Cout=%d is not supported by the tcgen05 path" % (K, Cin, Cout))
+    img = torch.empty(n, dtype=F32, device=weight.device)
+    call("insmos_conv_prep_weights_umma", _p(weight), K, Cin, Cout, _p(img), _stream())
+    if len(_WIMG_UMMA_CACHE) > 512:
+        _WIMG_UMMA_CACHE.clear()
+    _WIMG_UMMA_CACHE[key] = (img, weight)
+    return img
 
 _WFRAG_CACHE = {}
 
@@ -317,6 +356,9 @@ def sparse_conv(feat, weight, rb, scale=None, shift=None, bias=None, residual=No
         algo = DEFAULT_CONV_ALGO if Cout % 4 == 0 else 2
         if algo == 2 and Cin < 8 and Cout % 4 == 0 and Cout <= 16:
             algo = 1          # 1..7 input channels: a tensor-core k-step would be mostly padding; fp32 thread-per-pair
+        if (algo == 2 and USE_UMMA and Cin >= UMMA_MIN_CIN and Cout >= UMMA_MIN_COUT and K <= UMMA_MAX_K
+                and umma_eligible(K, Cin, Cout)):
+            algo = 4
     wf = prepared_weights(weight) if algo == 2 else None
     if _lib.PROFILE is not None:          # algorithmic bytes / flops of this launch (SURVEY 8d formula)
         P = rb.num_pairs
@@ -325,6 +367,9 @@ def sparse_conv(feat, weight, rb, scale=None, shift=None, bias=None, residual=No
     if algo == 1:
         call("insmos_sparse_conv_fwd_ffma", _p(feat), rb.n_in, Cin, _p(weight), K, Cout, _p(rb.seg), _p(rb.entries), rb.TM,
              _p(out), rb.n_out, C.byref(ep), _stream())
+    elif algo == 4:
+        call("insmos_sparse_conv_fwd_umma", _p(feat), rb.n_in, Cin, _p(prepared_weight_images(weight)), K, Cout, _p(rb.seg),
+             _p(rb.entries), rb.TM, _p(out), rb.n_out, C.byref(ep), _stream())
     elif algo == 3:
         call("insmos_sparse_conv_fwd", _p(feat), rb.n_in, Cin, _p(weight), K, Cout, _p(rb.seg), _p(rb.entries), rb.TM,
              _p(out), rb.n_out, C.byref(ep), 1, _stream())
@@ -439,7 +484,7 @@ def center_decode(cls, box, out_size_factor, vx, vy, x_min, y_min, hw=None):
 
 
 # dense BEV conv implementation: "tcgen05" (UTCHMMA + TMEM + TMA, bev_tcgen05.cu) or "mma" (mma.sync, bev.cu)
-BEV_IMPL = _os.environ.get("INSMOS_BEV_IMPL", "mma")
+BEV_IMPL = _os.environ.get("INSMOS_BEV_IMPL", "tcgen05")
 _WIMG_CACHE = {}
 
 

@@ -52,6 +52,57 @@ def test_sparse_conv_tile_sizes_and_epilogue(cuda, algo, TM):
     assert torch.allclose(out, ref, rtol=RTOL, atol=ATOL), (out - ref).abs().max()
 
 
+# ---- tcgen05 / TMEM path (algo 4): output-stationary implicit GEMM over 128-row super-tiles
+@pytest.mark.parametrize("Cin,Cout", [(16, 16), (19, 16), (32, 32), (35, 32), (64, 64), (67, 64), (64, 128), (128, 64),
+                                      (128, 128), (131, 128), (256, 128), (8, 48)])
+def test_sparse_conv_umma_matches_oracle(cuda, Cin, Cout):
+    cs, c, maps, rb = _setup(cuda, [3, 3, 3, 1])
+    g = torch.Generator().manual_seed(Cin * 1000 + Cout)
+    feats = torch.randn((len(c), Cin), generator=g)
+    W = torch.randn((27, Cin, Cout), generator=g) / np.sqrt(Cin * 10.0)
+    ref = me.conv(feats, W, maps, len(c))
+    out = ops.sparse_conv(feats.to(cuda), W.to(cuda), rb, algo=4).cpu()
+    err = (out - ref).abs().max().item()
+    assert torch.allclose(out, ref, rtol=RTOL, atol=ATOL), "max abs err %.3e (ref max %.3f)" % (err, ref.abs().max())
+
+
+@pytest.mark.parametrize("TM", [16, 32, 64, 128])
+@pytest.mark.parametrize("env", [{}, {"INSMOS_UMMA_NSPLIT": "2"}, {"INSMOS_UMMA_STAGES": "2"}, {"INSMOS_UMMA_STAGES": "3", "INSMOS_UMMA_NSPLIT": "4"}])
+def test_sparse_conv_umma_tile_sizes_epilogue_and_81_offsets(cuda, TM, env, monkeypatch):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    cs, c, maps, _ = _setup(cuda, [3, 3, 3, 3])
+    rb = ops.build_rulebook(cs, cs, ops.spec_me_cube([3, 3, 3, 3], [1, 1, 1, 1]), TM=TM)
+    g = torch.Generator().manual_seed(TM)
+    Cin, Cout = 48, 64
+    feats = torch.randn((len(c), Cin), generator=g)
+    W = torch.randn((81, Cin, Cout), generator=g) / 30.0
+    scale, shift = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g)
+    bias = torch.randn(Cout, generator=g)
+    res = torch.randn((len(c), Cout), generator=g)
+    ref = torch.relu(me.conv(feats, W, maps, len(c)) * scale + shift + bias + res)
+    out = ops.sparse_conv(feats.to(cuda), W.to(cuda), rb, scale=scale.to(cuda), shift=shift.to(cuda), bias=bias.to(cuda),
+                          residual=res.to(cuda), relu=True, algo=4).cpu()
+    assert torch.allclose(out, ref, rtol=RTOL, atol=ATOL), (out - ref).abs().max()
+
+
+def test_sparse_conv_umma_strided_and_transposed(cuda):
+    cs, c, _, _ = _setup(cuda, [3, 3, 3, 3])
+    co, _ = me.stride_coords(c, [2, 2, 2, 1])
+    cg, _ = ops.unique_coords(cs.coords, q=[2, 2, 2, 1])
+    maps = me.kernel_map(c, co, [2, 2, 2, 1], [1, 1, 1, 1])
+    g = torch.Generator().manual_seed(12)
+    feats = torch.randn((len(c), 32), generator=g)
+    W = torch.randn((8, 32, 64), generator=g) / 8.0
+    rb = ops.build_rulebook(cg, cs, ops.spec_me_cube([2, 2, 2, 1], [1, 1, 1, 1]))
+    ref = me.conv(feats, W, maps, len(co))
+    assert torch.allclose(ops.sparse_conv(feats.to(cuda), W.to(cuda), rb, algo=4).cpu(), ref, rtol=RTOL, atol=ATOL)
+    Wt = torch.randn((8, 64, 32), generator=g) / 8.0
+    rbt = ops.build_rulebook(cs, cg, ops.spec_me_up([2, 2, 2, 1], [2, 2, 2, 1], [1, 1, 1, 1]))
+    reft = me.conv(ref, Wt, me.transpose_map(maps), len(c))
+    assert torch.allclose(ops.sparse_conv(ref.to(cuda), Wt.to(cuda), rbt, algo=4).cpu(), reft, rtol=RTOL, atol=ATOL)
+
+
 def test_conv0_125_offsets_single_channel(cuda):
     cs, c, maps, rb = _setup(cuda, [5, 5, 5, 1])
     g = torch.Generator().manual_seed(3)
