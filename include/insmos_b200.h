@@ -209,7 +209,19 @@ int insmos_sparse_conv_fwd_umma(const float* in, int64_t n_in, int32_t Cin,
                                 const float* wimg, int32_t K, int32_t Cout,
                                 const uint16_t* seg, const uint32_t* entries, int32_t TM,
                                 float* out, int64_t n_out,
-                                const insmos_epilogue_t* ep, void* stream);
+                                const insmos_epilogue_t* ep,
+                                void* workspace, int64_t workspace_bytes, void* stream);
+/* Optional scratch for the call above ([dev], caller-owned, contents irrelevant, may be reused by later calls on the
+ * same stream): layers with few 128-row super-tiles split the kernel offsets over several CTAs and reduce the partial
+ * tiles through it in a fixed order.  0 = not needed; passing NULL only disables the split. */
+int64_t insmos_sparse_conv_umma_workspace_bytes(int64_t n_out, int32_t Cout);
+
+/* Dense 3x3 / pad 1 convolution of a channels-last image [H*W, Cin] (BEV backbone, base_bev_backbone.py:33-82, BatchNorm
+ * folded into weight/bias) through the same tcgen05 kernel as insmos_sparse_conv_fwd_umma: rows = pixels, arithmetic
+ * neighbour table.  wimg = insmos_conv_prep_weights_umma of the [9, Cin, Cout] weight; Cout % 16 == 0, Cout <= 128. */
+int insmos_conv2d_nhwc_umma(const float* in, int32_t H, int32_t W, int32_t Cin,
+                            const float* wimg, int32_t Cout, const float* bias, int32_t relu, float* out,
+                            void* workspace, int64_t workspace_bytes, void* stream);
 
 /* out[n,Cout] = in[n,Cin] . weight[Cin,Cout] + epilogue (ME kernel_size==1 conv, nn.Linear) */
 int insmos_linear_fwd(const float* in, int64_t n, int32_t Cin, const float* weight, int32_t Cout,

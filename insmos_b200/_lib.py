@@ -60,7 +60,9 @@ PROTOTYPES = {
     "insmos_conv_wimg_elems": (_I64, [_I32, _I32, _I32]),
     "insmos_conv_prep_weights_umma": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
     "insmos_sparse_conv_fwd_umma": (C.c_int, [_P, _I64, _I32, _P, _I32, _I32, _P, _P, _I32, _P, _I64,
-                                              C.POINTER(Epilogue), _P]),
+                                              C.POINTER(Epilogue), _P, _I64, _P]),
+    "insmos_sparse_conv_umma_workspace_bytes": (_I64, [_I64, _I32]),
+    "insmos_conv2d_nhwc_umma": (C.c_int, [_P, _I32, _I32, _I32, _P, _I32, _P, _I32, _P, _P, _I64, _P]),
     "insmos_linear_fwd": (C.c_int, [_P, _I64, _I32, _P, _I32, _P, C.POINTER(Epilogue), _P]),
     "insmos_affine_act": (C.c_int, [_P, _I64, _I32, _P, C.POINTER(Epilogue), _P]),
     "insmos_concat2": (C.c_int, [_P, _I32, _P, _I32, _I64, _P, _P]),

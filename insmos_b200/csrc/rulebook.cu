@@ -217,6 +217,56 @@ extern "C" int insmos_rulebook_build(const int32_t* out_coords, int64_t n_out,
     return rulebook_build_impl(out_coords, n_out, in_table, in_cap, nullptr, spec, TM, seg, entries, pair_count, stream);
 }
 
+// one block per tile, one thread per fine row: offset digit from the coordinates, parent row from the inverse map,
+// counting sort by offset inside the tile (bucket order = output-row order, as k_rulebook_tiles produces)
+__global__ void __launch_bounds__(128)
+k_rulebook_up(const int32_t* __restrict__ coords, int64_t n_out, const int32_t* __restrict__ parent,
+              insmos_mapspec_t spec, int TM, uint16_t* __restrict__ seg, uint32_t* __restrict__ entries,
+              unsigned long long* pair_count) {
+    __shared__ int kk[128];
+    __shared__ int hist[130];
+    const int K = spec.K, ncol = spec.ncol, ndim = spec.ndim;
+    const int tid = threadIdx.x;
+    const int64_t tile = blockIdx.x, row0 = tile * TM;
+    for (int k = tid; k <= K; k += 128) hist[k] = 0;
+    __syncthreads();
+    int k = -1, par = 0;
+    if (tid < TM && row0 + tid < n_out) {
+        const int32_t* c = coords + (row0 + tid) * ncol;
+        int dig[4] = {0, 0, 0, 0};
+        bool ok = true;
+        for (int d = 0; d < ndim; ++d) {
+            const int v = c[1 + d];
+            const int b0 = floor_div(v, spec.up_q[d]) * spec.up_q[d];
+            dig[d] = (v - b0) / spec.up_ts[d];
+            ok = ok && dig[d] < spec.ksize[d];
+        }
+        if (ok) {
+            k = 0;
+            if (spec.first_fastest) { for (int d = ndim - 1; d >= 0; --d) k = k * spec.ksize[d] + dig[d]; }
+            else { for (int d = 0; d < ndim; ++d) k = k * spec.ksize[d] + dig[d]; }
+            par = __ldg(parent + row0 + tid);
+            atomicAdd(&hist[k], 1);
+        }
+    }
+    if (tid < TM) kk[tid] = k;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int j = 0; j < K; ++j) { const int v = hist[j]; hist[j] = run; run += v; }
+        hist[K] = run;
+        if (pair_count && run) atomicAdd(pair_count, (unsigned long long)run);
+    }
+    __syncthreads();
+    uint16_t* tseg = seg + tile * (K + 1);
+    for (int j = tid; j <= K; j += 128) tseg[j] = (uint16_t)hist[j];
+    if (k >= 0) {
+        int rank = 0;
+        for (int r = 0; r < tid; ++r) rank += (kk[r] == k);
+        entries[tile * (int64_t)TM * K + hist[k] + rank] = ((uint32_t)tid << INSMOS_ROW_BITS) | (uint32_t)par;
+    }
+}
+
 // Transposed (up-sampling) map without hash probes: a fine row's only pair is (offset of the row inside its coarse
 // cell, its parent row), and the parent row is the inverse map that insmos_unique_coords(q) returned when the coarse
 // coordinate set was made.  Same rule-book layout / ordering as insmos_rulebook_build with a mode-1 spec.
@@ -224,5 +274,18 @@ extern "C" int insmos_rulebook_build_up(const int32_t* fine_coords, int64_t n_fi
                                         const insmos_mapspec_t* spec, int32_t TM,
                                         uint16_t* seg, uint32_t* entries, unsigned long long* pair_count, void* stream) {
     if (!parent) return INSMOS_ERR_INVALID_ARG;
+    if (fine_coords && spec && seg && entries && n_fine > 0 && spec->mode == 1 && spec->K >= 1 && spec->K <= 128 &&
+        (TM == 16 || TM == 32 || TM == 64 || TM == 128) && spec->ndim >= 1 && spec->ndim <= 4 &&
+        (spec->ncol == 4 || spec->ncol == 5) && spec->ndim <= spec->ncol - 1) {
+        int kprod = 1;
+        bool ok = true;
+        for (int d = 0; d < spec->ndim; ++d) { ok = ok && spec->ksize[d] >= 1 && spec->up_q[d] >= 1 && spec->up_ts[d] >= 1; kprod *= spec->ksize[d]; }
+        if (ok && kprod == spec->K) {
+            k_rulebook_up<<<(unsigned)ceil_div64(n_fine, TM), 128, 0, (cudaStream_t)stream>>>(
+                fine_coords, n_fine, parent, *spec, TM, seg, entries, pair_count);
+            INSMOS_CHECK_LAUNCH("k_rulebook_up");
+            return INSMOS_OK;
+        }
+    }
     return rulebook_build_impl(fine_coords, n_fine, nullptr, 1, parent, spec, TM, seg, entries, pair_count, stream);
 }

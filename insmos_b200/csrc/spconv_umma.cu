@@ -44,17 +44,18 @@ __device__ __forceinline__ float um_epilogue(float v, int c, int64_t row, int Co
     return v;
 }
 
+template <int S>                                                     // pipeline stages = producer groups (2 or 4)
 __global__ void __launch_bounds__(UM_THREADS)
 k_spconv_umma(UmArgs p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int K = p.K, TM = p.TM, G = p.G, NB = p.NB, S = p.stages, Cin = p.Cin;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic only: stays LDS/STS
+    const int K = p.K, TM = p.TM, G = p.G, NB = p.NB, Cin = p.Cin;
     const int b_bytes = NB * 128;                                    // one [NB x 32] weight image
     const int stage_bytes = 2 * UM_A_BYTES + 2 * b_bytes;
     int* nbr = reinterpret_cast<int*>(smem + (size_t)S * stage_bytes);   // [K][128]: in_row + 1, 0 = absent
     int* klist = nbr + K * UM_BM;                                    // [K] offsets with pairs in this super-tile
     int* meta = klist + K;                                           // [0] = number of active offsets
-    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(meta + 2) + 7) & ~(uintptr_t)7);   // full[], empty[], accumulator ready
+    uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 2 + ((K * (UM_BM + 1)) & 1));   // 8-byte aligned: full[], empty[], accumulator ready
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * UM_MAX_STAGES + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t stile = blockIdx.x / p.nsplit;
@@ -71,7 +72,7 @@ k_spconv_umma(UmArgs p) {
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(smem_u32(bars + s), UM_PROD_WARPS + 1);            // one arrive per producer warp + the TMA expect_tx arrive
+            mbar_init(smem_u32(bars + s), UM_PROD_WARPS / S + 1);        // one arrive per warp of the stage's group + the TMA expect_tx
             mbar_init(smem_u32(bars + UM_MAX_STAGES + s), 1);            // released by tcgen05.commit
         }
         mbar_init(smem_u32(bars + 2 * UM_MAX_STAGES), 1);
@@ -122,57 +123,70 @@ k_spconv_umma(UmArgs p) {
 
     if (warp < UM_PROD_WARPS) {
         // ---------------- gather producers ----------------
-        const int q = tid & 7;                                           // 16-byte chunk of the 128-byte row image
-        const int rb = tid >> 3;                                         // rows rb, rb+32, rb+64, rb+96
+        // The S stages are owned by S producer GROUPS of 8/S warps: group g fills stage g for the chunks c = g, g+S, ...
+        // A thread's fence.proxy.async waits for ALL its outstanding loads (ncu: the fence was the top stall when a
+        // thread prefetched the next chunk into registers), so the overlap of gather latency with split/store work
+        // has to come from different warps working on different stages.
+        constexpr int wg = UM_PROD_WARPS / S;                            // warps per group
+        constexpr int gthreads = wg * 32;
+        constexpr int rstep = gthreads >> 3;                             // 8 lanes per row: rows rb, rb + rstep, ...
+        constexpr int NR = UM_BM / rstep;                                // rows per thread and chunk: all gathers in flight at once
+        const int grp = warp / wg;
+        const int gt = tid - grp * gthreads;                             // thread index inside the group
+        const int q = gt & 7;                                            // 16-byte chunk of the 128-byte row image
+        const int rb = gt >> 3;
         const bool vec = (Cin & 3) == 0;
         const float* __restrict__ in = p.in;
-        float4 v[4];
-        auto load = [&](int c) {
-            const int k = klist[c / cchunks];
-            const int c0 = (c % cchunks) * UM_BK + 4 * q;
+        uint8_t* a_hi = smem + (size_t)grp * stage_bytes;
+        uint8_t* a_lo = a_hi + UM_A_BYTES;
+        const uint32_t bar_full = smem_u32(bars + grp), bar_empty = smem_u32(bars + UM_MAX_STAGES + grp);
+        int kidx = 0, kc = grp;                                          // chunk c = kidx * cchunks + kc
+        while (kc >= cchunks) { kc -= cchunks; ++kidx; }
+        uint32_t ph = 0;
+        for (int c = grp; c < nchunks; c += S) {
+            const int k = klist[kidx];
+            const int c0 = kc * UM_BK + 4 * q;
+            const int cw = min(UM_BK, Cin - kc * UM_BK);                 // channels of this chunk
+            const bool wr = q < 2 * ((cw + 7) >> 3);                     // 16-byte chunks the issued K-steps read
+            const int* nb = nbr + k * UM_BM;
+            {
+                float4 v[NR];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int src = nbr[k * UM_BM + rb + 32 * i];
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (src > 0 && c0 < Cin) {
-                    const float* x = in + (size_t)(src - 1) * Cin + c0;
-                    if (vec) v[i] = __ldg(reinterpret_cast<const float4*>(x));
-                    else {
-                        v[i].x = __ldg(x);
-                        if (c0 + 1 < Cin) v[i].y = __ldg(x + 1);
-                        if (c0 + 2 < Cin) v[i].z = __ldg(x + 2);
-                        if (c0 + 3 < Cin) v[i].w = __ldg(x + 3);
+                for (int i = 0; i < NR; ++i) {
+                    const int r = rb + i * rstep;
+                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int src = nb[r];
+                    if (src > 0 && c0 < Cin) {
+                        const float* x = in + (size_t)(src - 1) * Cin + c0;
+                        if (vec) v[i] = __ldg(reinterpret_cast<const float4*>(x));
+                        else {
+                            v[i].x = __ldg(x);
+                            if (c0 + 1 < Cin) v[i].y = __ldg(x + 1);
+                            if (c0 + 2 < Cin) v[i].z = __ldg(x + 2);
+                            if (c0 + 3 < Cin) v[i].w = __ldg(x + 3);
+                        }
                     }
                 }
-            }
-        };
-        if (nchunks > 0) load(0);
-        for (int c = 0; c < nchunks; ++c) {
-            const int s = c % S;
-            const uint32_t ph = (uint32_t)(c / S) & 1u;
-            float4 cur[4];
+                mbar_wait(bar_empty, ph ^ 1u);                           // stage free? (the gathers are already in flight)
+                if (wr) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) cur[i] = v[i];
-            if (c + 1 < nchunks) load(c + 1);                            // next chunk's gathers in flight
-            mbar_wait(smem_u32(bars + UM_MAX_STAGES + s), ph ^ 1u);      // stage free?
-            uint8_t* a_hi = smem + (size_t)s * stage_bytes;
-            uint8_t* a_lo = a_hi + UM_A_BYTES;
-            const int cw = min(UM_BK, Cin - (c % cchunks) * UM_BK);      // channels of this chunk
-            if (q < 2 * ((cw + 7) >> 3)) {                               // 16-byte chunks the issued K-steps read
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int r = rb + 32 * i;
-                    float4 h, l;
-                    split_rn(cur[i].x, h.x, l.x); split_rn(cur[i].y, h.y, l.y);
-                    split_rn(cur[i].z, h.z, l.z); split_rn(cur[i].w, h.w, l.w);
-                    const int off = r * 128 + ((q ^ (r & 7)) << 4);
-                    *reinterpret_cast<float4*>(a_hi + off) = h;
-                    *reinterpret_cast<float4*>(a_lo + off) = l;
+                    for (int i = 0; i < NR; ++i) {
+                        const int r = rb + i * rstep;
+                        float4 h, l;
+                        split_rn(v[i].x, h.x, l.x); split_rn(v[i].y, h.y, l.y);
+                        split_rn(v[i].z, h.z, l.z); split_rn(v[i].w, h.w, l.w);
+                        const int off = r * 128 + ((q ^ (r & 7)) << 4);
+                        *reinterpret_cast<float4*>(a_hi + off) = h;
+                        *reinterpret_cast<float4*>(a_lo + off) = l;
+                    }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(bars + s));              // one arrival per warp (256 serialized arrivals cost more than the stage)
+            if (lane == 0) mbar_arrive(bar_full);                        // one arrival per warp
+            ph ^= 1u;
+            kc += S;
+            while (kc >= cchunks) { kc -= cchunks; ++kidx; }
         }
         // ---------------- epilogue: TMEM -> registers -> BN / residual / ReLU -> global ----------------
         if (nchunks > 0) {
@@ -220,33 +234,35 @@ k_spconv_umma(UmArgs p) {
         // ---------------- TMA: weight images ----------------
         if (lane == 0) {
             const size_t img_floats = (size_t)p.Cout * 32;               // one [Cout x 32] image (hi or lo)
+            int s = 0, kidx = 0, kc = 0;
+            uint32_t ph = 0;
             for (int c = 0; c < nchunks; ++c) {
-                const int s = c % S;
-                const uint32_t ph = (uint32_t)(c / S) & 1u;
-                const int k = klist[c / cchunks], kc = c % cchunks;
+                const int k = klist[kidx];
                 mbar_wait(smem_u32(bars + UM_MAX_STAGES + s), ph ^ 1u);
                 const float* hi = p.wimg + ((size_t)k * cchunks + kc) * 2 * img_floats + (size_t)n0 * 32;
                 const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes + 2 * UM_A_BYTES);
                 mbar_arrive_expect_tx(smem_u32(bars + s), 2u * (uint32_t)b_bytes);
                 tma_bulk_g2s(dst, hi, (uint32_t)b_bytes, smem_u32(bars + s));
                 tma_bulk_g2s(dst + (uint32_t)b_bytes, hi + img_floats, (uint32_t)b_bytes, smem_u32(bars + s));
+                if (++s == S) { s = 0; ph ^= 1u; }
+                if (++kc == cchunks) { kc = 0; ++kidx; }
             }
         }
     } else {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32_m128(NB);
+            int s = 0, kc = 0, acc = 0;
+            uint32_t ph = 0;
             for (int c = 0; c < nchunks; ++c) {
-                const int s = c % S;
-                const uint32_t ph = (uint32_t)(c / S) & 1u;
                 mbar_wait(smem_u32(bars + s), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint64_t a_hi = umma_desc_sw128(base), a_lo = umma_desc_sw128(base + UM_A_BYTES);
                 const uint64_t b_hi = umma_desc_sw128(base + 2 * UM_A_BYTES), b_lo = umma_desc_sw128(base + 2 * UM_A_BYTES + b_bytes);
-                const int cw = min(UM_BK, Cin - (c % cchunks) * UM_BK);
+                const int cw = min(UM_BK, Cin - kc * UM_BK);
                 const int ksteps = (cw + 7) >> 3;
-                const uint32_t dacc = tmem_base + (uint32_t)((c % nacc) * NB);
+                const uint32_t dacc = tmem_base + (uint32_t)(acc * NB);
                 for (int j = 0; j < ksteps; ++j) {
                     const uint64_t adv = (uint64_t)(j * 2);                 // 32 bytes per K-step, in 16-byte units
                     umma_tf32(dacc, a_lo + adv, b_hi + adv, idesc, (c >= nacc || j != 0) ? 1u : 0u);
@@ -254,6 +270,9 @@ k_spconv_umma(UmArgs p) {
                     umma_tf32(dacc, a_hi + adv, b_hi + adv, idesc, 1u);
                 }
                 umma_commit(smem_u32(bars + UM_MAX_STAGES + s));            // stage reusable once these MMAs retire
+                if (++s == S) { s = 0; ph ^= 1u; }
+                if (++kc == cchunks) kc = 0;
+                if (++acc == nacc) acc = 0;
             }
             if (nchunks > 0) umma_commit(smem_u32(bars + 2 * UM_MAX_STAGES));   // accumulator complete
         }
@@ -262,6 +281,315 @@ k_spconv_umma(UmArgs p) {
     if (warp == UM_PROD_WARPS + 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TS variant: the gathered A operand goes to TENSOR MEMORY instead of shared memory.
+// Measured on B200 (tools/micro/umma_rate.cu, profiles/r01_umma_notes.md): a tcgen05.mma kind::tf32 M=128 K=8 occupies
+// the tensor pipe for ~75-86 cycles whatever N <= 128 is, i.e. ~1000 cycles per 32-channel chunk with the 3xTF32
+// products.  In the SS kernel above the MMA operand reads (6-8 KB per instruction), the producers' 32 KB of stores and
+// the TMA's weight tiles share the 128 B/clk shared-memory port and a chunk takes ~2000 cycles.  Here the producers
+// write the TF32 hi/lo rows straight into TMEM with tcgen05.st (thread = tile row = TMEM lane) and only the weight
+// tile is read from shared memory.  tcgen05.wait::st does not wait for global loads, so the next chunk's gathers stay
+// in flight in registers while the current one is split and stored.
+// TMEM map (512 columns): [0,256) four A stages (hi 32 | lo 32 columns each); [256, 256 + nacc*NB) accumulators.
+// Layers with few super-tiles split the active (offset, chunk) list over `ksplit` CTAs; the partial tiles go through
+// an L2-resident scratch buffer and the LAST CTA of a super-tile (atomic ticket) adds them in split order -- the
+// summation order is fixed, so results do not depend on scheduling -- and applies the epilogue.
+#define UT_STAGES 4
+
+struct UtArgs {
+    const float* in; const float* wimg; const uint16_t* seg; const uint32_t* entries; float* out;
+    float* partial; unsigned int* counters;
+    int64_t n_out, n_tiles, n_pad;
+    int Cin, Cout, K, TM, G, cchunks, nacc, ksplit, stages, tmem_cols;
+    int dense_H, dense_W;                                            // > 0: dense 3x3 pad-1 image convolution (rows = pixels), no rule book
+    insmos_epilogue_t ep;
+};
+
+__global__ void __launch_bounds__(UM_THREADS)
+k_spconv_umma_ts(UtArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int K = p.K, TM = p.TM, G = p.G, NB = p.Cout, Cin = p.Cin, nacc = p.nacc;
+    const int S = p.stages, slog = (S == 4) ? 2 : 1;                 // 2 or 4 stages (A in TMEM, B in shared memory)
+    const int acc_col = S * 64;                                      // accumulators follow the A stages
+    const int b_bytes = NB * 128;                                    // one [NB x 32] weight image
+    const int stage_bytes = 2 * b_bytes;                             // B hi | B lo
+    int* nbr = reinterpret_cast<int*>(smem + (size_t)S * stage_bytes);   // [K][128]: in_row + 1, 0 = absent
+    int* klist = nbr + K * UM_BM;
+    int* meta = klist + K;                                           // [0] active offsets, [1] "last CTA" flag
+    uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 2 + ((K * (UM_BM + 1)) & 1));   // full[4], empty[4], accumulator ready
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * UT_STAGES + 1);
+    uint16_t* sseg = reinterpret_cast<uint16_t*>(tmem_slot + 2);     // [G][K+1] copy of the tiles' bucket offsets
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t stile = blockIdx.x / p.ksplit;
+    const int sp = (int)(blockIdx.x - stile * p.ksplit);
+    const int64_t tile0 = stile * G;
+    const int ntile = (int)((p.n_tiles - tile0) < G ? (p.n_tiles - tile0) : G);
+
+    if (tid == 0) {
+        for (int s = 0; s < UT_STAGES; ++s) {
+            mbar_init(smem_u32(bars + s), 4 + 1);                        // 4 producer warps of the stage's group + the TMA expect_tx
+            mbar_init(smem_u32(bars + UT_STAGES + s), 1);                // released by tcgen05.commit
+        }
+        mbar_init(smem_u32(bars + 2 * UT_STAGES), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == UM_PROD_WARPS + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    const bool dense = p.dense_W > 0;
+    if (dense) {
+        // dense image mode (BEV 3x3 convolutions): the neighbour of pixel m at tap k is pixel m + dy*W + dx when in bounds
+        const int HW = p.dense_H * p.dense_W;
+        for (int i = tid; i < K * UM_BM; i += UM_THREADS) {
+            const int k = i / UM_BM, r = i - k * UM_BM;
+            const int64_t m = tile0 * TM + r;
+            int v = 0;
+            if (m < HW) {
+                const int py = (int)(m / p.dense_W), px = (int)(m - (int64_t)py * p.dense_W);
+                const int y = py + k / 3 - 1, x = px + k % 3 - 1;
+                if ((unsigned)y < (unsigned)p.dense_H && (unsigned)x < (unsigned)p.dense_W) v = y * p.dense_W + x + 1;
+            }
+            nbr[i] = v;
+        }
+        for (int k = tid; k < K; k += UM_THREADS) klist[k] = k;
+        if (tid == 0) { meta[0] = K; meta[1] = 0; }
+    } else {
+    for (int i = tid; i < K * UM_BM; i += UM_THREADS) nbr[i] = 0;
+    for (int i = tid; i < G * (K + 1); i += UM_THREADS) {
+        const int gi = i / (K + 1);
+        sseg[i] = (gi < ntile) ? p.seg[(tile0 + gi) * (K + 1) + (i - gi * (K + 1))] : (uint16_t)0;
+    }
+    __syncthreads();
+    // dense neighbour table: one thread per rule-book entry (all loads independent), its bucket by binary search
+    for (int gi = 0; gi < ntile; ++gi) {
+        const uint16_t* ts = sseg + gi * (K + 1);
+        const int tot = ts[K];
+        const uint32_t* tent = p.entries + (tile0 + gi) * (int64_t)TM * K;
+        for (int e = tid; e < tot; e += UM_THREADS) {
+            const uint32_t ent = __ldg(tent + e);
+            int lo = 0, hi = K;                                          // largest k with ts[k] <= e
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((int)ts[mid] <= e) lo = mid; else hi = mid; }
+            nbr[lo * UM_BM + gi * TM + (int)(ent >> INSMOS_ROW_BITS)] = (int)(ent & INSMOS_ROW_MASK) + 1;
+        }
+    }
+    }
+    if (warp == 0 && !dense) {
+        int cnt = 0;
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            const int k = k0 + lane;
+            int tot = 0;
+            if (k < K)
+                for (int gi = 0; gi < ntile; ++gi) tot += (int)sseg[gi * (K + 1) + k + 1] - (int)sseg[gi * (K + 1) + k];
+            const unsigned bal = __ballot_sync(0xffffffffu, tot > 0);
+            if (tot > 0) klist[cnt + __popc(bal & ((1u << lane) - 1u))] = k;
+            cnt += __popc(bal);
+        }
+        if (lane == 0) { meta[0] = cnt; meta[1] = 0; }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    const int cchunks = p.cchunks;
+    const int ntotal = meta[0] * cchunks;
+    const int c_begin = (int)(((int64_t)sp * ntotal) / p.ksplit), c_end = (int)(((int64_t)(sp + 1) * ntotal) / p.ksplit);
+    const int nloc = c_end - c_begin;                                // chunks of this CTA
+    const int kidx0 = c_begin / cchunks, kc0 = c_begin - kidx0 * cchunks;
+
+    if (warp < UM_PROD_WARPS) {
+        // ---------------- gather producers: thread = tile row = TMEM lane; group g takes local chunks g, g+2, ... ----------------
+        const int grp = warp >> 2;
+        const int r = (warp & 3) * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const bool vec = (Cin & 3) == 0;
+        const float* __restrict__ in = p.in;
+        float4 v[8];
+        auto issue = [&](int kidx, int kc) {
+            const int src = nbr[klist[kidx] * UM_BM + r];
+            const int c0 = kc * UM_BK;
+            const int cw = min(UM_BK, Cin - c0);
+            const float* x = in + (size_t)(src > 0 ? src - 1 : 0) * Cin + c0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (src > 0 && 4 * j < cw) {
+                    if (vec) v[j] = __ldg(reinterpret_cast<const float4*>(x + 4 * j));
+                    else {
+                        v[j].x = __ldg(x + 4 * j);
+                        if (4 * j + 1 < cw) v[j].y = __ldg(x + 4 * j + 1);
+                        if (4 * j + 2 < cw) v[j].z = __ldg(x + 4 * j + 2);
+                        if (4 * j + 3 < cw) v[j].w = __ldg(x + 4 * j + 3);
+                    }
+                }
+            }
+        };
+        int kidx = kidx0, kc = kc0 + grp;                                // (offset index, channel chunk) of local chunk i
+        while (kc >= cchunks) { kc -= cchunks; ++kidx; }
+        if (grp < nloc) issue(kidx, kc);
+        for (int i = grp; i < nloc; i += 2) {
+            const int s = i & (S - 1);
+            const uint32_t ph = (uint32_t)(i >> slog) & 1u;
+            const int cw = min(UM_BK, Cin - kc * UM_BK);
+            const int ksteps = (cw + 7) >> 3;
+            float4 cur[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cur[j] = v[j];
+            kc += 2;
+            while (kc >= cchunks) { kc -= cchunks; ++kidx; }
+            if (i + 2 < nloc) issue(kidx, kc);                           // next chunk's gathers stay in flight
+            mbar_wait(smem_u32(bars + UT_STAGES + s), ph ^ 1u);          // A columns and B tile of the stage are free
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = lane_addr + (uint32_t)(s * 64), a_lo = a_hi + 32u;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (h * 2 < ksteps) {                                    // warp-uniform: tcgen05.st is warp-collective
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 x = cur[h * 4 + j];
+                        float a, b;
+                        split_rn(x.x, a, b); hi[4 * j + 0] = __float_as_uint(a); lo[4 * j + 0] = __float_as_uint(b);
+                        split_rn(x.y, a, b); hi[4 * j + 1] = __float_as_uint(a); lo[4 * j + 1] = __float_as_uint(b);
+                        split_rn(x.z, a, b); hi[4 * j + 2] = __float_as_uint(a); lo[4 * j + 2] = __float_as_uint(b);
+                        split_rn(x.w, a, b); hi[4 * j + 3] = __float_as_uint(a); lo[4 * j + 3] = __float_as_uint(b);
+                    }
+                    tmem_st16(a_hi + (uint32_t)(h * 16), hi);
+                    tmem_st16(a_lo + (uint32_t)(h * 16), lo);
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(bars + s));
+        }
+        // ---------------- epilogue ----------------
+        if (nloc > 0) {
+            mbar_wait(smem_u32(bars + 2 * UT_STAGES), 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const int halves = (NB % 32) == 0 ? 2 : 1;                       // warps 4-7 take the upper half of the columns
+        const int hcols = NB / halves;
+        const int half = warp >> 2;
+        const int64_t row = tile0 * TM + r;
+        const uint32_t taddr = lane_addr + (uint32_t)(acc_col + half * hcols);
+        const bool mine = half < halves;
+        const bool direct = p.ksplit == 1;
+        if (mine) {
+#pragma unroll 1
+            for (int cb = 0; cb < hcols; cb += 16) {
+                uint32_t rr[16];
+                if (nloc > 0) tmem_ld16(taddr + (uint32_t)cb, rr);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) rr[j] = 0u;
+                }
+                for (int a = 1; a < nacc && a <= nloc; ++a) {            // accumulators that received products
+                    uint32_t r2[16];
+                    tmem_ld16(taddr + (uint32_t)(a * NB + cb), r2);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint(__uint_as_float(rr[j]) + __uint_as_float(r2[j]));
+                }
+                if (row < p.n_out) {
+                    const int cbase = half * hcols + cb;
+                    float* dst = direct ? p.out + row * NB + cbase : p.partial + ((int64_t)sp * p.n_pad + row) * NB + cbase;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float4 o = make_float4(__uint_as_float(rr[4 * j]), __uint_as_float(rr[4 * j + 1]),
+                                               __uint_as_float(rr[4 * j + 2]), __uint_as_float(rr[4 * j + 3]));
+                        if (direct) {
+                            o.x = um_epilogue(o.x, cbase + 4 * j + 0, row, NB, p.ep); o.y = um_epilogue(o.y, cbase + 4 * j + 1, row, NB, p.ep);
+                            o.z = um_epilogue(o.z, cbase + 4 * j + 2, row, NB, p.ep); o.w = um_epilogue(o.w, cbase + 4 * j + 3, row, NB, p.ep);
+                        }
+                        *reinterpret_cast<float4*>(dst + 4 * j) = o;
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (!direct) {
+            // ticket: the CTA that arrives last owns the reduction of the super-tile's ksplit partial tiles
+            __threadfence();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tid == 0) {
+                const unsigned int old = atomicAdd(p.counters + stile, 1u);
+                meta[1] = (old == (unsigned int)(p.ksplit - 1)) ? 1 : 0;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (*reinterpret_cast<volatile int*>(meta + 1) && mine && row < p.n_out) {
+                __threadfence();
+#pragma unroll 1
+                for (int cb = 0; cb < hcols; cb += 4) {
+                    const int cbase = half * hcols + cb;
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int q = 0; q < p.ksplit; ++q) {                 // fixed order: scheduling-independent result
+                        const float4 t = __ldcg(reinterpret_cast<const float4*>(p.partial + ((int64_t)q * p.n_pad + row) * NB + cbase));
+                        o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+                    }
+                    o.x = um_epilogue(o.x, cbase + 0, row, NB, p.ep); o.y = um_epilogue(o.y, cbase + 1, row, NB, p.ep);
+                    o.z = um_epilogue(o.z, cbase + 2, row, NB, p.ep); o.w = um_epilogue(o.w, cbase + 3, row, NB, p.ep);
+                    *reinterpret_cast<float4*>(p.out + row * NB + cbase) = o;
+                }
+            }
+        }
+    } else if (warp == UM_PROD_WARPS) {
+        // ---------------- TMA: weight images ----------------
+        if (lane == 0) {
+            const size_t img_floats = (size_t)NB * 32;
+            int kidx = kidx0, kc = kc0;
+            for (int i = 0; i < nloc; ++i) {
+                const int s = i & (S - 1);
+                const uint32_t ph = (uint32_t)(i >> slog) & 1u;
+                mbar_wait(smem_u32(bars + UT_STAGES + s), ph ^ 1u);
+                const float* hi = p.wimg + ((size_t)klist[kidx] * cchunks + kc) * 2 * img_floats;
+                const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes);
+                mbar_arrive_expect_tx(smem_u32(bars + s), 2u * (uint32_t)b_bytes);
+                tma_bulk_g2s(dst, hi, 2u * (uint32_t)b_bytes, smem_u32(bars + s));      // hi and lo images are adjacent
+                if (++kc == cchunks) { kc = 0; ++kidx; }
+            }
+        }
+    } else {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32_m128(NB);
+            int kc = kc0, acc = 0;
+            for (int i = 0; i < nloc; ++i) {
+                const int s = i & (S - 1);
+                const uint32_t ph = (uint32_t)(i >> slog) & 1u;
+                mbar_wait(smem_u32(bars + s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint64_t b_hi = umma_desc_sw128(base), b_lo = umma_desc_sw128(base + b_bytes);
+                const uint32_t a_hi = tmem_base + (uint32_t)(s * 64), a_lo = a_hi + 32u;
+                const int cw = min(UM_BK, Cin - kc * UM_BK);
+                const int ksteps = (cw + 7) >> 3;
+                // accumulator 0 takes the two small cross products (|a_lo*b_hi|, |a_hi*b_lo| ~ 2^-11 |a*b|), accumulators
+                // 1..nacc-1 take the a_hi*b_hi products round-robin: the tensor core truncates on every accumulate, so the
+                // drift is proportional to the number of adds into a LARGE accumulator (tools/umma_accuracy.py)
+                const uint32_t dsmall = tmem_base + (uint32_t)acc_col;
+                const uint32_t dbig = tmem_base + (uint32_t)(acc_col + (nacc > 1 ? 1 + acc : 0) * NB);
+                const bool big_first = (nacc > 1) ? (i < nacc - 1) : false;
+                for (int j = 0; j < ksteps; ++j) {
+                    const uint64_t adv = (uint64_t)(j * 2);
+                    umma_tf32_ts(dsmall, a_lo + (uint32_t)(8 * j), b_hi + adv, idesc, (i != 0 || j != 0) ? 1u : 0u);
+                    umma_tf32_ts(dsmall, a_hi + (uint32_t)(8 * j), b_lo + adv, idesc, 1u);
+                    umma_tf32_ts(dbig, a_hi + (uint32_t)(8 * j), b_hi + adv, idesc, (big_first && j == 0) ? 0u : 1u);
+                }
+                umma_commit(smem_u32(bars + UT_STAGES + s));
+                if (++kc == cchunks) kc = 0;
+                if (++acc >= nacc - 1) acc = 0;
+            }
+            if (nloc > 0) umma_commit(smem_u32(bars + 2 * UT_STAGES));
+        }
+    }
+    __syncthreads();
+    if (warp == UM_PROD_WARPS + 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
 }
 
@@ -307,11 +635,66 @@ extern "C" int insmos_conv_prep_weights_umma(const float* weight, int32_t K, int
     return INSMOS_OK;
 }
 
+// launch configuration of the TS kernel (shared by the sparse and the dense-image entry points)
+static int launch_umma_ts(UtArgs& t, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
+    const int Cout = t.Cout, K = t.K;
+    struct { int64_t n_tiles; int G; int cchunks; } a = {t.n_tiles, t.G, t.cchunks};
+        const int64_t st = ceil_div64(a.n_tiles, a.G);
+        t.n_pad = st * UM_BM;
+        // TMEM budget: S A-stages of 64 columns + nacc accumulators of Cout columns, power of two.  Cout <= 64 fits in 256
+        // columns with 2 stages, so two CTAs share an SM and overlap each other's prologue / epilogue; Cout = 128 takes all 512.
+        t.stages = Cout <= 64 ? 2 : 4;
+        if (const char* e = getenv("INSMOS_UMMA_STAGES")) { const int v = atoi(e); if (v == 2 || v == 4) t.stages = v; }
+        const int acc_budget = (t.stages == 2 ? 256 : 512) - t.stages * 64;
+        t.nacc = 4;
+        while (t.nacc > 1 && Cout * t.nacc > acc_budget) t.nacc /= 2;
+        if (const char* e = getenv("INSMOS_UMMA_NACC")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && Cout * v <= acc_budget) t.nacc = v; }
+        t.tmem_cols = 32;
+        while (t.tmem_cols < t.stages * 64 + Cout * t.nacc) t.tmem_cols <<= 1;
+        const size_t smem_ts = 1024 + (size_t)t.stages * 2 * Cout * 128 + sizeof(int) * ((size_t)K * UM_BM + K + 4) +
+                               8 * (2 * UT_STAGES + 1) + 8 + 16 + 2 * (size_t)a.G * (K + 1) + 16;
+        const int per_sm = (t.tmem_cols <= 256 && 2 * (smem_ts + 1024) <= 227 * 1024) ? 2 : 1;
+        // offsets split over CTAs while the layer cannot fill the machine, as long as every CTA keeps >= 8 chunks
+        int ksplit = (int)((148 * per_sm) / st);
+        if (ksplit > 4) ksplit = 4;
+        if (ksplit > (K * a.cchunks) / 8) ksplit = (K * a.cchunks) / 8;
+        if (ksplit < 1) ksplit = 1;
+        if (const char* e = getenv("INSMOS_UMMA_KSPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 4) ksplit = v; }
+        const int64_t need = 256 + st * 4 + (int64_t)ksplit * t.n_pad * Cout * 4;
+        if (ksplit > 1 && (!workspace || workspace_bytes < need)) ksplit = 1;
+        t.ksplit = ksplit;
+        t.counters = nullptr; t.partial = nullptr;
+        if (ksplit > 1) {
+            t.counters = reinterpret_cast<unsigned int*>(workspace);
+            t.partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + ((st * 4 + 255) / 256) * 256);
+            INSMOS_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)st * 4, stream));
+        }
+        if (smem_ts <= 227 * 1024) {
+            static thread_local size_t configured_ts = 0;
+            if (smem_ts > configured_ts) {
+                INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_spconv_umma_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ts));
+                configured_ts = smem_ts;
+            }
+            k_spconv_umma_ts<<<(unsigned)(st * ksplit), UM_THREADS, smem_ts, stream>>>(t);
+            INSMOS_CHECK_LAUNCH("k_spconv_umma_ts");
+            return INSMOS_OK;
+        }
+    return INSMOS_ERR_UNSUPPORTED;
+}
+
+extern "C" int64_t insmos_sparse_conv_umma_workspace_bytes(int64_t n_out, int32_t Cout) {
+    if (n_out <= 0 || Cout <= 0) return 0;
+    const int64_t stiles = ceil_div64(n_out, UM_BM);
+    if (stiles >= 148) return 0;                                      // enough super-tiles: no offset split
+    return 256 + stiles * 4 + 4 * stiles * UM_BM * (int64_t)Cout * 4;
+}
+
 extern "C" int insmos_sparse_conv_fwd_umma(const float* in, int64_t n_in, int32_t Cin,
                                            const float* wimg, int32_t K, int32_t Cout,
                                            const uint16_t* seg, const uint32_t* entries, int32_t TM,
                                            float* out, int64_t n_out,
-                                           const insmos_epilogue_t* ep_in, void* stream) {
+                                           const insmos_epilogue_t* ep_in,
+                                           void* workspace, int64_t workspace_bytes, void* stream) {
     if ((n_in > 0 && !in) || !wimg || !seg || !entries || (n_out > 0 && !out) || n_out < 0 || n_in < 0) return INSMOS_ERR_INVALID_ARG;
     if (TM != 16 && TM != 32 && TM != 64 && TM != 128) return INSMOS_ERR_INVALID_ARG;
     if (!umma_shape_ok(K, Cin, Cout)) return INSMOS_ERR_UNSUPPORTED;
@@ -324,6 +707,16 @@ extern "C" int insmos_sparse_conv_fwd_umma(const float* in, int64_t n_in, int32_
     if (ep_in) a.ep = *ep_in;
     if (a.ep.scale && !a.ep.shift) return INSMOS_ERR_INVALID_ARG;
     if (n_out == 0) return INSMOS_OK;
+    static const bool force_ss = getenv("INSMOS_UMMA_SS") != nullptr;     // A/B switch: operands from shared memory
+    if (!force_ss && Cout <= 128) {
+        UtArgs t;
+        t.in = in; t.wimg = wimg; t.seg = seg; t.entries = entries; t.out = out;
+        t.n_out = n_out; t.n_tiles = a.n_tiles;
+        t.Cin = Cin; t.Cout = Cout; t.K = K; t.TM = TM; t.G = a.G; t.cchunks = a.cchunks; t.ep = a.ep;
+        t.dense_H = 0; t.dense_W = 0;
+        const int rc = launch_umma_ts(t, workspace, workspace_bytes, (cudaStream_t)stream);
+        if (rc != INSMOS_ERR_UNSUPPORTED) return rc;
+    }
     const int64_t stiles = ceil_div64(a.n_tiles, a.G);
     // split the output channels over CTAs while the layer has too few super-tiles to fill 148 SMs (the gather is
     // repeated per split, the MMA work is not)
@@ -337,11 +730,11 @@ extern "C" int insmos_sparse_conv_fwd_umma(const float* in, int64_t n_in, int32_
     if (a.NB > 128) { a.nsplit = Cout / 128; a.NB = 128; if (Cout % 128) return INSMOS_ERR_UNSUPPORTED; }
     const size_t stage_bytes = 2 * (size_t)UM_A_BYTES + 2 * (size_t)a.NB * 128;
     const size_t fixed = 1024 + sizeof(int) * ((size_t)K * UM_BM + K + 2) + 8 * (2 * UM_MAX_STAGES + 1) + 8 + 16;
-    int stages = UM_MAX_STAGES;
-    while (stages > 2 && fixed + stages * stage_bytes > 220 * 1024) --stages;
+    int stages = UM_MAX_STAGES;                                       // 2 or 4: the 8 producer warps are split into `stages` groups
+    if (fixed + stages * stage_bytes > 220 * 1024) stages = 2;
     // many CTAs: two resident CTAs per SM (each with a 2-stage ring) overlap each other's gather latency
     if (stiles * a.nsplit > 148 && fixed + 2 * stage_bytes <= 112 * 1024) stages = 2;
-    if (const char* e = getenv("INSMOS_UMMA_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= UM_MAX_STAGES) stages = v; }
+    if (const char* e = getenv("INSMOS_UMMA_STAGES")) { const int v = atoi(e); if (v == 2 || v == 4) stages = v; }
     const size_t smem = fixed + stages * stage_bytes;
     if (smem > 227 * 1024) return INSMOS_ERR_UNSUPPORTED;
     a.stages = stages;
@@ -350,12 +743,30 @@ extern "C" int insmos_sparse_conv_fwd_umma(const float* in, int64_t n_in, int32_
     while (nacc > 1 && a.NB * nacc * ctas_per_sm > 512) nacc /= 2;
     if (const char* e = getenv("INSMOS_UMMA_NACC")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && a.NB * v <= 512) nacc = v; }
     a.nacc = nacc;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_spconv_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    static thread_local size_t configured[2] = {0, 0};
+    auto kern = stages == 4 ? k_spconv_umma<4> : k_spconv_umma<2>;
+    if (smem > configured[stages == 4]) {
+        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[stages == 4] = smem;
     }
-    k_spconv_umma<<<(unsigned)(stiles * a.nsplit), UM_THREADS, smem, (cudaStream_t)stream>>>(a);
+    kern<<<(unsigned)(stiles * a.nsplit), UM_THREADS, smem, (cudaStream_t)stream>>>(a);
     INSMOS_CHECK_LAUNCH("k_spconv_umma");
     return INSMOS_OK;
+}
+
+// Dense 3x3 / pad 1 image convolution (BEV backbone, base_bev_backbone.py:33-82 with BatchNorm folded) through the same
+// kernel: rows = pixels of the channels-last [H*W, Cin] image, the neighbour table is arithmetic instead of a rule book.
+// wimg: insmos_conv_prep_weights_umma of the [9, Cin, Cout] weight.
+extern "C" int insmos_conv2d_nhwc_umma(const float* in, int32_t H, int32_t W, int32_t Cin,
+                                       const float* wimg, int32_t Cout, const float* bias, int32_t relu, float* out,
+                                       void* workspace, int64_t workspace_bytes, void* stream) {
+    if (!in || !wimg || !out || H <= 0 || W <= 0) return INSMOS_ERR_INVALID_ARG;
+    if (!umma_shape_ok(9, Cin, Cout) || Cout > 128 || (int64_t)H * W > (int64_t)INSMOS_ROW_MASK) return INSMOS_ERR_UNSUPPORTED;
+    UtArgs t;
+    t.in = in; t.wimg = wimg; t.seg = nullptr; t.entries = nullptr; t.out = out;
+    t.n_out = (int64_t)H * W; t.TM = UM_BM; t.G = 1; t.n_tiles = ceil_div64(t.n_out, UM_BM);
+    t.Cin = Cin; t.Cout = Cout; t.K = 9; t.cchunks = (Cin + UM_BK - 1) / UM_BK;
+    t.ep = insmos_epilogue_t{nullptr, nullptr, bias, nullptr, relu};
+    t.dense_H = H; t.dense_W = W;
+    return launch_umma_ts(t, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -368,8 +368,10 @@ def sparse_conv(feat, weight, rb, scale=None, shift=None, bias=None, residual=No
         call("insmos_sparse_conv_fwd_ffma", _p(feat), rb.n_in, Cin, _p(weight), K, Cout, _p(rb.seg), _p(rb.entries), rb.TM,
              _p(out), rb.n_out, C.byref(ep), _stream())
     elif algo == 4:
+        wsb = _lib.load().insmos_sparse_conv_umma_workspace_bytes(rb.n_out, Cout)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=feat.device) if wsb > 0 else None
         call("insmos_sparse_conv_fwd_umma", _p(feat), rb.n_in, Cin, _p(prepared_weight_images(weight)), K, Cout, _p(rb.seg),
-             _p(rb.entries), rb.TM, _p(out), rb.n_out, C.byref(ep), _stream())
+             _p(rb.entries), rb.TM, _p(out), rb.n_out, C.byref(ep), _p(ws) if ws is not None else None, wsb, _stream())
     elif algo == 3:
         call("insmos_sparse_conv_fwd", _p(feat), rb.n_in, Cin, _p(weight), K, Cout, _p(rb.seg), _p(rb.entries), rb.TM,
              _p(out), rb.n_out, C.byref(ep), 1, _stream())
@@ -483,8 +485,9 @@ def center_decode(cls, box, out_size_factor, vx, vy, x_min, y_min, hw=None):
     return boxes, scores, labels
 
 
-# dense BEV conv implementation: "tcgen05" (UTCHMMA + TMEM + TMA, bev_tcgen05.cu) or "mma" (mma.sync, bev.cu)
-BEV_IMPL = _os.environ.get("INSMOS_BEV_IMPL", "tcgen05")
+# dense BEV conv implementation: "umma" (3x3 convs through the TMEM-operand kernel of spconv_umma.cu, the rest as "tcgen05"),
+# "tcgen05" (UTCHMMA + TMEM + TMA, operands in shared memory, bev_tcgen05.cu) or "mma" (mma.sync, bev.cu)
+BEV_IMPL = _os.environ.get("INSMOS_BEV_IMPL", "umma")
 _WIMG_CACHE = {}
 
 
@@ -513,7 +516,11 @@ def conv2d_nhwc(x, H, W, weight, mode, bias=None, relu=False, impl=None):
     out = torch.empty(((4 if mode == 2 else 1) * H * W, Cout), dtype=F32, device=x.device)
     if bias is not None:
         bias = _req(bias, F32, "conv2d_nhwc")
-    if (impl or BEV_IMPL) == "tcgen05":
+    which = impl or BEV_IMPL
+    if which == "umma" and mode == 0 and umma_eligible(taps, Cin, Cout) and Cout <= 128:
+        call("insmos_conv2d_nhwc_umma", _p(x), H, W, Cin, _p(prepared_weight_images(weight)), Cout, _p(bias), 1 if relu else 0,
+             _p(out), None, 0, _stream())
+    elif which in ("tcgen05", "umma"):
         img = bev_weight_images(weight)
         call("insmos_conv2d_nhwc_tcgen05", _p(x), H, W, Cin, _p(img), mode, Cout, _p(bias), 1 if relu else 0, _p(out), _stream())
     else:

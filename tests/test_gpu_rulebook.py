@@ -35,12 +35,19 @@ def test_me_strided_and_transposed_maps_all_levels(cuda):
     fine_g, fine_o, ts = cs, c, 1
     for _ in range(3):
         coarse_o, _ = me.stride_coords(fine_o, [2 * ts, 2 * ts, 2 * ts, 1])
-        coarse_g, _ = ops.unique_coords(fine_g.coords, q=[2 * ts, 2 * ts, 2 * ts, 1])
+        coarse_g, parent = ops.unique_coords(fine_g.coords, q=[2 * ts, 2 * ts, 2 * ts, 1])
         maps = me.kernel_map(fine_o, coarse_o, [2, 2, 2, 1], [ts, ts, ts, 1])
         rb = ops.build_rulebook(coarse_g, fine_g, ops.spec_me_cube([2, 2, 2, 1], [ts, ts, ts, 1]))
         _check(rb, maps, len(fine_o), len(coarse_o))
         rbt = ops.build_rulebook(fine_g, coarse_g, ops.spec_me_up([2, 2, 2, 1], [2, 2, 2, 1], [ts, ts, ts, 1]))
         _check(rbt, me.transpose_map(maps), len(coarse_o), len(fine_o))
+        # probe-free build from the parent map: identical rule book, bit for bit, at every tile size
+        for TM in (None, 16, 64):
+            a = ops.build_rulebook(fine_g, coarse_g, ops.spec_me_up([2, 2, 2, 1], [2, 2, 2, 1], [ts, ts, ts, 1]), TM=TM)
+            b = ops.build_rulebook(fine_g, coarse_g, ops.spec_me_up([2, 2, 2, 1], [2, 2, 2, 1], [ts, ts, ts, 1]), TM=TM, parent=parent)
+            assert a.num_pairs == b.num_pairs == len(fine_o)
+            assert torch.equal(a.seg, b.seg)
+            assert np.array_equal(a.to_coo().numpy(), b.to_coo().numpy())
         # 3^4 map at the coarse level (offsets scaled by the tensor stride, time stride stays 1)
         ts2 = 2 * ts
         rb3 = ops.build_rulebook(coarse_g, coarse_g, ops.spec_me_cube([3, 3, 3, 3], [ts2, ts2, ts2, 1]))
