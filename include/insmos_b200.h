@@ -160,6 +160,21 @@ int insmos_rulebook_build(const int32_t* out_coords, int64_t n_out,
                           uint16_t* seg, uint32_t* entries, unsigned long long* pair_count,
                           int32_t* counters, void* stream);
 
+/* X-block table of a coordinate set: one 32-byte slot per (floor(x/xstep) >> 2, other coordinates) holding the rows of
+ * the block's 4 voxels.  The cube kernel maps (ME 5x5x5x1, 3x3x3x3; minkunet.py:55-60,71-128) probe runs of consecutive
+ * x, which cost 1-2 slot lookups here instead of 3-5 voxel-table probes.  table: insmos_xblock_capacity(n) slots of
+ * 32 bytes, [dev], caller-owned; coordinates must be multiples of xstep in x (a set at tensor stride xstep) and inside
+ * the packable range already checked by insmos_voxelize4d / insmos_unique_coords. */
+int64_t insmos_xblock_capacity(int64_t n);
+int insmos_xblock_build(const int32_t* coords, int64_t n, int32_t ncol, int32_t xstep, void* table, int64_t cap, void* stream);
+/* insmos_rulebook_build through the x-block table (mode-0 spec with q = 1, a[0] = 1, e[0] = xstep, first dimension
+ * fastest, 3 <= ksize[0] <= 8; INSMOS_ERR_UNSUPPORTED otherwise).  Output identical to insmos_rulebook_build. */
+int insmos_rulebook_build_xb(const int32_t* out_coords, int64_t n_out,
+                             const insmos_slot_t* in_table, int64_t in_cap,
+                             const void* xtable, int64_t xcap, int32_t xstep,
+                             const insmos_mapspec_t* spec, int32_t TM,
+                             uint16_t* seg, uint32_t* entries, unsigned long long* pair_count, void* stream);
+
 /* Transposed (MinkowskiConvolutionTranspose, kernel == stride) map built without hash probes: the only pair of fine row
  * i is (offset of i inside its coarse cell, parent[i]) where parent is the inverse map insmos_unique_coords(q) returned
  * when the coarse set was made (ME derives the same map by swapping the strided one: minkunet.py:96-125).  `spec` is the

@@ -48,6 +48,9 @@ PROTOTYPES = {
                                     _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "insmos_rulebook_entries_capacity": (_I64, [_I64, _I32, _I32]),
     "insmos_rulebook_build": (C.c_int, [_P, _I64, _P, _I64, C.POINTER(MapSpec), _I32, _P, _P, _P, _P, _P]),
+    "insmos_xblock_capacity": (_I64, [_I64]),
+    "insmos_xblock_build": (C.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P]),
+    "insmos_rulebook_build_xb": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, C.POINTER(MapSpec), _I32, _P, _P, _P, _P]),
     "insmos_rulebook_build_up": (C.c_int, [_P, _I64, _P, C.POINTER(MapSpec), _I32, _P, _P, _P, _P]),
     "insmos_sparse_conv_fwd": (C.c_int, [_P, _I64, _I32, _P, _I32, _I32, _P, _P, _I32, _P, _I64,
                                          C.POINTER(Epilogue), _I32, _P]),
@@ -120,6 +123,9 @@ KERNELS_PER_CALL = {
     "insmos_affine_act": 1, "insmos_concat2": 1, "insmos_pairsum_add": 1, "insmos_gather_rows": 1,
     "insmos_segment_mean": 2, "insmos_build_current_points": 1, "insmos_dense_scatter": 1, "insmos_center_decode": 1,
     "insmos_nms_rotated": 2, "insmos_boxes_to_voxel_units": 1, "insmos_box_membership": 3,
+    "insmos_xblock_build": 2, "insmos_rulebook_build_xb": 1, "insmos_rulebook_build_up": 1,
+    "insmos_sparse_conv_fwd_umma": 1, "insmos_conv2d_nhwc_umma": 1, "insmos_conv2d_nhwc_tcgen05": 1, "insmos_conv2d_nhwc_tc": 1,
+    "insmos_conv_prep_weights_umma": 1, "insmos_bev_prep_weights_tcgen05": 1, "insmos_dense_scatter_nhwc": 1,
 }
 PROFILE = None        # list collecting (name, start_event, end_event, meta) when profiling is on
 NEXT_META = None      # ops sets this right before a call to attach algorithmic bytes / flops
@@ -135,7 +141,13 @@ def profile_stop():
     global PROFILE
     import torch
     torch.cuda.synchronize()
-    out = [(n, s.elapsed_time(e), m) for n, s, e, m in PROFILE]
+    out, prev = [], None
+    for n, s, e, m in PROFILE:
+        m = dict(m) if m else {}
+        if prev is not None:
+            m["gap_ms"] = round(prev.elapsed_time(s), 4)       # device idle (or torch kernels) between two C-ABI calls
+        out.append((n, s.elapsed_time(e), m))
+        prev = e
     PROFILE = None
     return out
 

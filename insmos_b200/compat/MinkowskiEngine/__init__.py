@@ -40,10 +40,13 @@ class CoordinateManager:
         self.rulebooks = {}
         self.parents = {}       # (fine key, coarse key) -> int32 [n_fine] row of each fine voxel's coarse cell
 
-    def stride(self, key, stride):
+    def stride(self, key, stride, lazy=False):
+        """coordinate map at tensor stride key*stride (made on first use).  lazy=True queues the kernel and leaves the
+        row count on the device until the set is first used (see ops.CoordSet): callers that know the set will be
+        needed later (insmos_b200.net.motion) request it one level ahead."""
         new_key = tuple(k * s for k, s in zip(key, stride))
         if new_key not in self.sets:
-            cs, parent = ops.unique_coords(self.sets[key].coords, q=list(new_key))
+            cs, parent = ops.unique_coords(self.sets[key].coords, q=list(new_key), lazy=lazy)
             self.sets[new_key] = cs
             self.parents[(key, new_key)] = parent
         return new_key
@@ -58,7 +61,9 @@ class CoordinateManager:
                 spec = ops.spec_me_up(list(ksize), list(stride), list(out_key))
             # transposed map: the coarse set was made from the fine one, so every fine row already knows its parent
             parent = self.parents.get((out_key, in_key)) if kind == "up" else None
-            rb = ops.build_rulebook(self.sets[out_key], self.sets[in_key], spec, parent=parent)
+            # every set of this manager holds coordinates that are multiples of its tensor stride -> x-block probing
+            rb = ops.build_rulebook(self.sets[out_key], self.sets[in_key], spec, parent=parent,
+                                    xstep=in_key[0] if kind == "conv" else None)
             self.rulebooks[k] = rb
         return rb
 

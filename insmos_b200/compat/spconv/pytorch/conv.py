@@ -60,6 +60,16 @@ class SparseConvolution(SparseModule):
             self._wk = (ver, wk)
         return self._wk[1]
 
+    def prefetch_indices(self, in_set, in_shape, indice_dict):
+        """queue the output-coordinate kernel of a strided SparseConv3d ahead of its forward (row count read lazily,
+        see ops.CoordSet); forward() then finds the indice data under indice_key.  Returns the IndiceData."""
+        assert not self.subm and not self.inverse and self.indice_key is not None
+        out_shape = [(i + 2 * p - k) // s + 1 for i, k, s, p in zip(in_shape, self.kernel_size, self.stride, self.padding)]
+        out_set = ops.spconv_out_coords(in_set, self.kernel_size, self.stride, self.padding, out_shape, lazy=True)
+        data = IndiceData(in_set, out_set, self.kernel_size, self.stride, self.padding, in_shape, out_shape, False)
+        indice_dict[self.indice_key] = data
+        return data
+
     def forward(self, x, bn=None, relu=False, residual=None, algo=0):
         assert isinstance(x, SparseConvTensor)
         scale = shift = None

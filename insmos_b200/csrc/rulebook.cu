@@ -33,12 +33,83 @@ __device__ __forceinline__ int64_t packed_delta(int d0, int d1, int d2, int d3) 
     return (int64_t)d0 + (int64_t)d1 * 65536ll + (int64_t)d2 * 4294967296ll + (int64_t)d3 * 281474976710656ll;
 }
 
+// ------------------------------------------------------------------------------------------------
+// X-BLOCK TABLE.  The cube maps probe runs of 3 or 5 consecutive x for every (row, other-dims offset): with the voxel
+// table every probe is an independent random 16-byte access (ncu: the map build is bound by the divergent probe
+// loop, ~100 M probes per forward).  A second table keyed by (x_index >> 2, y, z, t) holds the rows of the 4 voxels of
+// an x-block in one 32-byte slot, so a run costs 1-2 slot lookups instead of 3-5.  x_index = floor(x / xstep) with
+// xstep = tensor stride of the set (coordinates of a strided level are multiples of it).
+struct __align__(32) XBlockSlot { unsigned long long key; int32_t rows[4]; unsigned long long pad; };
+
+__global__ void k_xblock_clear(XBlockSlot* table, int64_t cap) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) {
+        int4* q = reinterpret_cast<int4*>(table + i);
+        q[0] = make_int4(-1, -1, -1, -1);                          // key = all ones, rows[0..1] = -1
+        q[1] = make_int4(-1, -1, 0, 0);                            // rows[2..3] = -1
+    }
+}
+__global__ void k_xblock_insert(const int32_t* __restrict__ coords, int64_t n, int ncol, int xstep,
+                                XBlockSlot* table, uint64_t mask) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t* c = coords + i * ncol;
+    const int xi = floor_div(c[1], xstep);
+    const uint64_t key = pack_key(c[0], xi >> 2, ncol > 2 ? c[2] : 0, ncol > 3 ? c[3] : 0, ncol > 4 ? c[4] : 0);
+    uint64_t slot = hash64(key) & mask;
+    while (true) {
+        unsigned long long* kp = &table[slot].key;
+        const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
+        if (cur == key) break;
+        if (cur == INSMOS_EMPTY_KEY) {
+            const unsigned long long prev = atomicCAS(kp, INSMOS_EMPTY_KEY, (unsigned long long)key);
+            if (prev == INSMOS_EMPTY_KEY || prev == key) break;
+        }
+        slot = (slot + 1) & mask;
+    }
+    table[slot].rows[xi & 3] = (int32_t)i;
+}
+extern "C" int64_t insmos_xblock_capacity(int64_t n) {
+    int64_t cap = 1024;
+    while (cap < 2 * n) cap <<= 1;                                 // slots hold up to 4 voxels: load <= 0.5 even with 1 voxel per block
+    return cap;
+}
+extern "C" int insmos_xblock_build(const int32_t* coords, int64_t n, int32_t ncol, int32_t xstep,
+                                   void* table, int64_t cap, void* stream) {
+    if (!table || cap <= 0 || (cap & (cap - 1)) || (n > 0 && !coords) || n < 0 || xstep < 1 || ncol < 2 || ncol > 5)
+        return INSMOS_ERR_INVALID_ARG;
+    if (cap < 2 * n) return INSMOS_ERR_INVALID_ARG;
+    k_xblock_clear<<<(unsigned)ceil_div64(cap, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<XBlockSlot*>(table), cap);
+    INSMOS_CHECK_LAUNCH("k_xblock_clear");
+    if (n > 0) {
+        k_xblock_insert<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(
+            coords, n, ncol, xstep, reinterpret_cast<XBlockSlot*>(table), (uint64_t)(cap - 1));
+        INSMOS_CHECK_LAUNCH("k_xblock_insert");
+    }
+    return INSMOS_OK;
+}
+// rows of the x-block with packed key `key` (all -1 when the block is absent); two 16-byte loads per probe step
+__device__ __forceinline__ int4 xblock_find(const XBlockSlot* __restrict__ table, uint64_t mask, uint64_t key) {
+    uint64_t slot = hash64(key) & mask;
+    while (true) {
+        const int4 v0 = __ldg(reinterpret_cast<const int4*>(table + slot));
+        const uint64_t k = ((uint64_t)(uint32_t)v0.y << 32) | (uint32_t)v0.x;
+        if (k == key) {
+            const int4 v1 = __ldg(reinterpret_cast<const int4*>(table + slot) + 1);
+            return make_int4(v0.z, v0.w, v1.x, v1.y);
+        }
+        if (k == INSMOS_EMPTY_KEY) return make_int4(-1, -1, -1, -1);
+        slot = (slot + 1) & mask;
+    }
+}
+
 __global__ void __launch_bounds__(RB_THREADS)
 k_rulebook_tiles(const int32_t* __restrict__ out_coords, int64_t n_out,
                  const insmos_slot_t* __restrict__ table, uint64_t mask,
                  insmos_mapspec_t spec, int TM,
                  uint16_t* __restrict__ seg, uint32_t* __restrict__ entries,
-                 unsigned long long* pair_count, const int32_t* __restrict__ parent) {
+                 unsigned long long* pair_count, const int32_t* __restrict__ parent,
+                 const XBlockSlot* __restrict__ xtable, uint64_t xmask, int xstep) {
     extern __shared__ __align__(16) int smem[];
     const int K = spec.K, ncol = spec.ncol, ndim = spec.ndim;
     int* nbr = smem;                                            // [TM*K] in-row or -1
@@ -91,6 +162,58 @@ k_rulebook_tiles(const int32_t* __restrict__ out_coords, int64_t n_out,
         __syncthreads();
     }
 
+    // ---- phase A (x-block table): lanes run over the offset GROUPS (all dimensions but x), warps over rows; a lane
+    // resolves the ksize[0] consecutive x of its group with one or two 32-byte slot lookups.
+    if (xtable && fast) {
+        const int kx = spec.ksize[0], ng = K / kx;
+        for (int r = warp; r < TM; r += nwarps) {
+            const bool row_ok = (row0 + r) < n_out;
+            const int64_t base = rbase[r];
+            if (row_ok && base == -2) {                              // near the edge of the packable range: checked path, voxel table
+                const int* c = tc + r * 5;
+                for (int k = lane; k < K; k += 32) {
+                    int ci[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) if (d < ndim) ci[d] = c[1 + d] * spec.a[d] + kd[k * 4 + d];
+                    int res = -1;
+                    if (coord_in_range(c[0], ci[0], ci[1], ci[2], ci[3]))
+                        res = table_find_row(table, mask, pack_key(c[0], ci[0], ci[1], ci[2], ci[3]));
+                    nbr[r * K + k] = res;
+                    if (res >= 0) atomicAdd(&hist[k], 1);
+                }
+                continue;
+            }
+            for (int g = lane; g < ng; g += 32) {
+                int res[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) res[j] = -1;
+                if (row_ok && base >= 0) {
+                    const uint64_t key0 = (uint64_t)(base + delta[g * kx]);          // voxel key of the run's first x
+                    const int x0 = (int)(key0 & 0xffffull) - 32768;
+                    const int xi0 = floor_div(x0, xstep);
+                    const uint64_t rest = key0 & ~0xffffull;
+                    const int b_first = xi0 >> 2, b_last = (xi0 + kx - 1) >> 2;
+                    for (int b = b_first; b <= b_last; ++b) {
+                        const int4 rows = xblock_find(xtable, xmask, rest | (uint64_t)(uint32_t)(b + 32768));
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int xi = xi0 + j;
+                            if (j < kx && (xi >> 2) == b) {
+                                const int sub = xi & 3;
+                                res[j] = sub == 0 ? rows.x : sub == 1 ? rows.y : sub == 2 ? rows.z : rows.w;
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j < kx) {
+                        nbr[r * K + g * kx + j] = res[j];
+                        if (res[j] >= 0) atomicAdd(&hist[g * kx + j], 1);
+                    }
+            }
+        }
+    } else
     // ---- phase A: probe.  Lanes run over offsets, warps over rows.
     for (int r = warp; r < TM; r += nwarps) {
         const bool row_ok = (row0 + r) < n_out;
@@ -169,7 +292,8 @@ k_rulebook_tiles(const int32_t* __restrict__ out_coords, int64_t n_out,
 static int rulebook_build_impl(const int32_t* out_coords, int64_t n_out,
                                const insmos_slot_t* in_table, int64_t in_cap, const int32_t* parent,
                                const insmos_mapspec_t* spec, int32_t TM,
-                               uint16_t* seg, uint32_t* entries, unsigned long long* pair_count, void* stream) {
+                               uint16_t* seg, uint32_t* entries, unsigned long long* pair_count, void* stream,
+                               const void* xtable = nullptr, int64_t xcap = 0, int32_t xstep = 0) {
     if (!out_coords || !spec || !seg || !entries || n_out < 0) return INSMOS_ERR_INVALID_ARG;
     if (parent) {
         if (spec->mode != 1) return INSMOS_ERR_INVALID_ARG;
@@ -203,7 +327,8 @@ static int rulebook_build_impl(const int32_t* out_coords, int64_t n_out,
     }
     const int64_t n_tiles = ceil_div64(n_out, TM);
     k_rulebook_tiles<<<(unsigned)n_tiles, RB_THREADS, smem, (cudaStream_t)stream>>>(
-        out_coords, n_out, in_table, (uint64_t)(in_cap - 1), *spec, TM, seg, entries, pair_count, parent);
+        out_coords, n_out, in_table, (uint64_t)(in_cap - 1), *spec, TM, seg, entries, pair_count, parent,
+        reinterpret_cast<const XBlockSlot*>(xtable), (uint64_t)(xcap > 0 ? xcap - 1 : 0), xstep);
     INSMOS_CHECK_LAUNCH("k_rulebook_tiles");
     return INSMOS_OK;
 }
@@ -288,4 +413,20 @@ extern "C" int insmos_rulebook_build_up(const int32_t* fine_coords, int64_t n_fi
         }
     }
     return rulebook_build_impl(fine_coords, n_fine, nullptr, 1, parent, spec, TM, seg, entries, pair_count, stream);
+}
+
+// Same map as insmos_rulebook_build for an affine cube spec whose x runs are contiguous (mode 0, q = 1, a[0] = 1,
+// e[0] = xstep, first dimension fastest, 3 <= ksize[0] <= 8), probing the x-block table of the input set.  Bit-identical
+// output; the voxel table is still needed for rows at the edge of the packable coordinate range.
+extern "C" int insmos_rulebook_build_xb(const int32_t* out_coords, int64_t n_out,
+                                        const insmos_slot_t* in_table, int64_t in_cap,
+                                        const void* xtable, int64_t xcap, int32_t xstep,
+                                        const insmos_mapspec_t* spec, int32_t TM,
+                                        uint16_t* seg, uint32_t* entries, unsigned long long* pair_count, void* stream) {
+    if (!xtable || !spec || xcap <= 0 || (xcap & (xcap - 1)) || xstep < 1) return INSMOS_ERR_INVALID_ARG;
+    if (spec->mode != 0 || !spec->first_fastest || spec->a[0] != 1 || spec->e[0] != xstep || spec->ksize[0] < 3 || spec->ksize[0] > 8)
+        return INSMOS_ERR_UNSUPPORTED;
+    for (int d = 0; d < spec->ndim; ++d) if (spec->q[d] != 1) return INSMOS_ERR_UNSUPPORTED;
+    return rulebook_build_impl(out_coords, n_out, in_table, in_cap, nullptr, spec, TM, seg, entries, pair_count, stream,
+                               xtable, xcap, xstep);
 }

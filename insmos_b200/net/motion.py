@@ -81,8 +81,14 @@ class CustomMinkUNet(nn.Module):
         return conv(x, bn=bn, relu=True)
 
     def forward(self, x):                                       # minkunet.py:139-181
+        # the strided coordinate maps are requested one level ahead of their first use, so that the host read of
+        # each map's row count happens while the GPU is busy with the previous level (no drained queue)
+        mgr, s = x.coordinate_manager, self.conv1p1s2.stride
+        k2 = mgr.stride(x.coordinate_map_key, s, lazy=True)
         p1 = self._cbr(self.conv0p1s1, self.bn0, x)
+        k4 = mgr.stride(k2, s, lazy=True)
         b1p2 = self.block1(self._cbr(self.conv1p1s2, self.bn1, p1))
+        mgr.stride(k4, s, lazy=True)
         b2p4 = self.block2(self._cbr(self.conv2p2s2, self.bn2, b1p2))
         out = self.block3(self._cbr(self.conv3p4s2, self.bn3, b2p4))
         out = self.block6(ME.cat(self._cbr(self.convtr5p8s2, self.bntr5, out), b2p4))

@@ -137,10 +137,18 @@ class UNetV2(nn.Module):
         feats, coords = batch_dict["voxel_features"], batch_dict["voxel_coords"]
         x = spconv.SparseConvTensor(features=feats, indices=coords.int(), spatial_shape=self.sparse_shape, batch_size=1,
                                     coordset=batch_dict.get("_voxel_set"))
+        # the output coordinates of every strided convolution are queued one level ahead of its forward: the host read
+        # of their count then overlaps the previous level's kernels instead of draining the queue
+        down = [m for seq in (self.conv2, self.conv3, self.conv4, self.conv_out) for m in seq.modules()
+                if isinstance(m, spconv.SparseConv3d)]
+        d = down[0].prefetch_indices(x.coordset, x.spatial_shape, x.indice_dict)
         x = self.conv_input(x)
         x_conv1 = self.conv1(x)
+        d = down[1].prefetch_indices(d.out_set, d.out_shape, x.indice_dict)
         x_conv2 = self.conv2(x_conv1)
+        d = down[2].prefetch_indices(d.out_set, d.out_shape, x.indice_dict)
         x_conv3 = self.conv3(x_conv2)
+        down[3].prefetch_indices(d.out_set, d.out_shape, x.indice_dict)
         x_conv4 = self.conv4(x_conv3)
         out = self.conv_out(x_conv4)
         batch_dict["encoded_spconv_tensor"] = out

@@ -15,7 +15,14 @@ I32 = torch.int32
 F32 = torch.float32
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    # torch.cuda.current_stream() costs ~16 us of Python per call (cProfile on the GPU host: 2.2 ms per forward over
+    # 136 C-ABI calls); the raw getter returns the same cudaStream_t handle in well under a microsecond
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(torch._C._cuda_getDevice()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -47,14 +54,41 @@ def _scan_scratch(n, device):
     return torch.empty(_lib.load().insmos_scan_scratch_bytes(int(n)), dtype=torch.uint8, device=device)
 
 
+LAZY_SETS = __import__("os").environ.get("INSMOS_LAZY_SETS", "0") != "0"     # deferred count reads: measured no gain on B200 (124.5 vs 123 scans/s), off by default
+
+
 class CoordSet:
     """Unique integer coordinates [n, ncol] (batch first) plus the hash table that maps a
-    coordinate to its row.  Equivalent of an ME coordinate-map key / spconv indices."""
+    coordinate to its row.  Equivalent of an ME coordinate-map key / spconv indices.
 
-    def __init__(self, coords, n, table, cap, tensor_stride=None):
-        self.coords, self.n, self.table, self.cap = coords, int(n), table, int(cap)
+    A set made with lazy=True keeps its row count on the device until `n` / `coords` is first read: the kernel that
+    produces it is queued, the caller queues independent work behind it, and the one host read of the counter then
+    finds the GPU busy instead of draining the queue (each eager read cost a ~65 us bubble in the C2 forward)."""
+
+    def __init__(self, coords, n, table, cap, tensor_stride=None, pending=None):
+        self._coords, self._n = coords, (None if n is None else int(n))
+        self.table, self.cap = table, int(cap)
         self.tensor_stride = tensor_stride
         self.ncol = coords.shape[1]
+        self._pending = pending                 # (counters tensor, name, clone flag) until resolved
+
+    def _resolve(self):
+        if self._pending is not None:
+            counters, what, clone = self._pending
+            self._pending = None
+            c = _read_counters(counters, what)
+            self._n = int(c[_lib.CNT_ROWS])
+            self._coords = self._coords[:self._n].clone() if clone else self._coords[:self._n]
+
+    @property
+    def n(self):
+        self._resolve()
+        return self._n
+
+    @property
+    def coords(self):
+        self._resolve()
+        return self._coords
 
 
 def _new_table(n, device):
@@ -83,8 +117,9 @@ def voxelize4d(points, quant):
     return CoordSet(coords[:nv], nv, table, cap), inverse[:n], cur[:nc]
 
 
-def unique_coords(coords, q=None):
-    """unique int32 rows [N,ncol] in first-occurrence order (optionally floored to multiples of q)."""
+def unique_coords(coords, q=None, lazy=False):
+    """unique int32 rows [N,ncol] in first-occurrence order (optionally floored to multiples of q).
+    lazy=True: the row count stays on the device until the returned set's n / coords is read."""
     coords = _req(coords, I32, "unique_coords")
     n, ncol = coords.shape
     dev = coords.device
@@ -96,13 +131,15 @@ def unique_coords(coords, q=None):
     qa = None if q is None else _arr(C.c_int32, [int(v) for v in q])
     call("insmos_unique_coords", _p(coords), n, ncol, qa, _p(table), cap, _p(slot), _p(out), _p(inverse),
          _p(counters), _p(_scan_scratch(n, dev)), _stream())
+    if lazy and LAZY_SETS:
+        return CoordSet(out, None, table, cap, pending=(counters, "unique_coords", False)), inverse[:n]
     c = _read_counters(counters, "unique_coords")
     nv = c[_lib.CNT_ROWS]
     return CoordSet(out[:nv], nv, table, cap), inverse[:n]
 
 
-def spconv_out_coords(in_set, ksize, stride, pad, out_shape):
-    """output coordinates of a strided spconv SparseConv3d (oracle order)."""
+def spconv_out_coords(in_set, ksize, stride, pad, out_shape, lazy=False):
+    """output coordinates of a strided spconv SparseConv3d (oracle order); lazy as in unique_coords."""
     lib = _lib.load()
     n = in_set.n
     K = int(ksize[0] * ksize[1] * ksize[2])
@@ -114,6 +151,8 @@ def spconv_out_coords(in_set, ksize, stride, pad, out_shape):
     call("insmos_spconv_out_coords", _p(in_set.coords), n, _arr(C.c_int32, list(ksize)), _arr(C.c_int32, list(stride)),
          _arr(C.c_int32, list(pad)), _arr(C.c_int32, list(out_shape)), _p(table), cap, _p(out), _p(counters),
          _p(scratch), _stream())
+    if lazy and LAZY_SETS:
+        return CoordSet(out, None, table, cap, pending=(counters, "spconv_out_coords", True))
     c = _read_counters(counters, "spconv_out_coords")
     nv = c[_lib.CNT_ROWS]
     return CoordSet(out[:nv].clone(), nv, table, cap)
@@ -237,10 +276,30 @@ def choose_tile_rows(n_out, K):
     return tm
 
 
-def build_rulebook(out_set, in_set, spec, TM=None, parent=None):
+import os as _os
+
+USE_XBLOCK = _os.environ.get("INSMOS_XBLOCK", "1") != "0"
+# measured on B200 (C2 workload): 5-wide x runs 683 -> 404 us, 3-wide runs no gain (295 -> 277, 112 -> 124 us)
+XBLOCK_MIN_KX = int(_os.environ.get("INSMOS_XBLOCK_MIN_KX", "5"))
+
+
+def xblock_table(cs, xstep):
+    """x-block table of a CoordSet whose x coordinates are multiples of xstep (cached on the set)."""
+    cache = cs.__dict__.setdefault("_xblock", {})
+    hit = cache.get(xstep)
+    if hit is None:
+        cap = _lib.load().insmos_xblock_capacity(max(cs.n, 1))
+        table = torch.empty((cap, 4), dtype=torch.int64, device=cs.coords.device)
+        call("insmos_xblock_build", _p(cs.coords), cs.n, cs.ncol, int(xstep), _p(table), cap, _stream())
+        hit = cache[xstep] = (table, cap)
+    return hit
+
+
+def build_rulebook(out_set, in_set, spec, TM=None, parent=None, xstep=None):
     """tiled rule book of the map in_set -> out_set.  parent (int32 [n_out], optional): for a transposed map (mode-1
     spec) the row of every output (fine) row's coarse cell in in_set, as returned by unique_coords(q): the map is then
-    built without hash probes."""
+    built without hash probes.  xstep (optional): tensor stride of in_set in x (its x coordinates are multiples of it):
+    cube maps with >= 3 offsets in x then probe the set's x-block table."""
     lib = _lib.load()
     K = int(spec.K)
     n_out = out_set.n
@@ -253,10 +312,18 @@ def build_rulebook(out_set, in_set, spec, TM=None, parent=None):
     pc = torch.zeros(1, dtype=torch.int64, device=dev)
     if in_set.n > (1 << _lib.ROW_BITS):
         raise RuntimeError("insmos_b200.build_rulebook: more than 2^25 input rows")
+    use_xb = (USE_XBLOCK and parent is None and xstep is not None and spec.mode == 0 and spec.first_fastest == 1
+              and spec.a[0] == 1 and spec.e[0] == int(xstep) and XBLOCK_MIN_KX <= spec.ksize[0] <= 8
+              and all(spec.q[d] == 1 for d in range(spec.ndim)))
+    if use_xb:
+        xt, xcap = xblock_table(in_set, int(xstep))      # (its own C-ABI call: before the profile meta is armed)
     prof = _lib.PROFILE is not None
     if prof:
         _lib.NEXT_META = {"n_out": n_out, "K": K, "ncol": out_set.ncol}
-    if parent is not None:
+    if use_xb:
+        call("insmos_rulebook_build_xb", _p(out_set.coords), n_out, _p(in_set.table), in_set.cap, _p(xt), xcap, int(xstep),
+             C.byref(spec), TM, _p(seg), _p(entries), _p(pc), _stream())
+    elif parent is not None:
         parent = _req(parent, I32, "build_rulebook.parent")
         if parent.shape[0] != n_out:
             raise ValueError("build_rulebook: parent must have one entry per output row")

@@ -30,6 +30,27 @@ def test_me_cube_maps(cuda, ksize, TM):
     _check(rb, me.kernel_map(c, c, ksize, [1, 1, 1, 1]), len(c), len(c))
 
 
+@pytest.mark.parametrize("ksize", [[3, 3, 3, 3], [5, 5, 5, 1], [3, 3, 3, 1]])
+def test_me_cube_maps_xblock_table_identical(cuda, ksize, monkeypatch):
+    """x-block probing must reproduce the voxel-table rule book bit for bit, at every level (coordinates = multiples of ts)."""
+    monkeypatch.setattr(ops, "XBLOCK_MIN_KX", 3)          # also exercise the 3-wide runs (off by default: no speed-up)
+    cs, c = _levels(cuda)
+    g, ts = cs, 1
+    for _ in range(3):
+        for TM in (None, 16):
+            spec = ops.spec_me_cube(ksize, [ts, ts, ts, 1])
+            a = ops.build_rulebook(g, g, spec, TM=TM)
+            b = ops.build_rulebook(g, g, spec, TM=TM, xstep=ts)
+            assert a.num_pairs == b.num_pairs
+            assert torch.equal(a.seg, b.seg)
+            tot = int(a.seg.view(torch.int16).to(torch.int32).view(-1, a.K + 1)[:, -1].sum())   # occupied prefixes only
+            assert np.array_equal(a.to_coo().numpy(), b.to_coo().numpy())
+        if ts == 1:
+            _check(b, me.kernel_map(c, c, ksize, [1, 1, 1, 1]), len(c), len(c))
+        g, _ = ops.unique_coords(g.coords, q=[2 * ts, 2 * ts, 2 * ts, 1])
+        ts *= 2
+
+
 def test_me_strided_and_transposed_maps_all_levels(cuda):
     cs, c = _levels(cuda)
     fine_g, fine_o, ts = cs, c, 1
