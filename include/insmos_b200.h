@@ -319,6 +319,23 @@ int insmos_boxes_to_voxel_units(const float* boxes7, const int32_t* labels, int3
 int insmos_box_membership(const int32_t* coords, int64_t n, const float* boxes8, int32_t nb, float mult,
                           float* out, int32_t out_stride, int32_t* first_hit, void* stream);
 
+/* ---- steps either side of the forward path ---------------------------- */
+
+/* N1 input staging (scripts/predict_mos.py:114-159 DemoDataset.__getitem__, :161-166 transform_point_cloud, :174-179
+ * timestamp_tensor): raw scans concatenated oldest -> newest as [total,4] f32 (x,y,z,intensity), scan s occupying rows
+ * [scan_offsets[s], scan_offsets[s+1]) (int64 [n_scans+1], [dev]); transforms = n_scans row-major 4x4 float64
+ * inv(to_pose) @ from_pose ([dev], may be NULL when apply_transform == 0); timestamps f32 [n_scans] ([dev]).
+ * out [total,5] f32 (x,y,z,intensity,t): xyz = float32(T @ (x,y,z,1)) evaluated in float64 like the reference. */
+int insmos_stage_scans(const float* raw_xyzi, const int64_t* scan_offsets, int32_t n_scans,
+                       const double* transforms, const float* timestamps, int32_t apply_transform,
+                       float* out_xyzit, int64_t total_points, void* stream);
+
+/* N2 output labelling (scripts/predict_mos.py:440-454, :279-283): logits [n,n_class] f32 -> classes in ignore_mask
+ * (bit c = class c) to -inf, softmax, confidence [n,n_class-1] (columns 1..), argmax (first maximum), labels[n] =
+ * label_map[argmax] (int32 [n_class], [dev]; NULL = identity).  confidence may be NULL. */
+int insmos_mos_labels(const float* logits, int64_t n, int32_t n_class, uint32_t ignore_mask,
+                      const int32_t* label_map, int32_t* labels, float* confidence, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,8 @@ PROTOTYPES = {
     "insmos_bev_wimg_elems": (_I64, [_I32, _I32, _I32]),
     "insmos_bev_prep_weights_tcgen05": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
     "insmos_conv2d_nhwc_tcgen05": (C.c_int, [_P, _I32, _I32, _I32, _P, _I32, _I32, _P, _I32, _P, _P]),
+    "insmos_stage_scans": (C.c_int, [_P, _P, _I32, _P, _P, _I32, _P, _I64, _P]),
+    "insmos_mos_labels": (C.c_int, [_P, _I64, _I32, C.c_uint32, _P, _P, _P, _P]),
     "insmos_nms_rotated": (C.c_int, [_P, _I32, _F, _I32, _P, _P, _P, _P]),
     "insmos_boxes_to_voxel_units": (C.c_int, [_P, _P, _I32, C.POINTER(_F), C.POINTER(_F), _F, _P, _P]),
     "insmos_box_membership": (C.c_int, [_P, _I64, _P, _I32, _F, _P, _I32, _P, _P]),

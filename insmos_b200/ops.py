@@ -645,3 +645,31 @@ def box_membership(coords, boxes8, mult, out=None, out_stride=None, col_offset=0
         call("insmos_box_membership", _p(coords), n, _p(boxes8), nb, float(mult), base, int(out_stride), _p(first),
              _stream())
     return out
+
+
+# ---- steps either side of the forward path -------------------------------------
+def stage_scans(raw, offsets, transforms, stamps, out=None):
+    """raw [total,4] f32 (x,y,z,intensity), offsets int64 [n+1], transforms f64 [n,4,4] or None, stamps f32 [n]
+    (all CUDA) -> [total,5] f32 (x,y,z,intensity,t) in the newest scan's frame (predict_mos.py:114-159)."""
+    raw = _req(raw, F32, "stage_scans")
+    n_scans = int(stamps.shape[0])
+    total = int(raw.shape[0])
+    if offsets.dtype != torch.int64 or offsets.numel() != n_scans + 1 or stamps.dtype != F32:
+        raise TypeError("stage_scans: offsets must be int64 [n_scans+1], stamps float32 [n_scans]")
+    if transforms is not None and (transforms.dtype != torch.float64 or tuple(transforms.shape) != (n_scans, 4, 4)):
+        raise TypeError("stage_scans: transforms must be float64 [n_scans,4,4]")
+    if out is None:
+        out = torch.empty((total, 5), dtype=F32, device=raw.device)
+    call("insmos_stage_scans", _p(raw), _p(offsets.contiguous()), n_scans, _p(None if transforms is None else transforms.contiguous()),
+         _p(stamps.contiguous()), 0 if transforms is None else 1, _p(out), total, _stream())
+    return out
+
+
+def mos_labels(logits, ignore_mask, label_map=None, want_confidence=True):
+    """logits [n,C] f32 -> (labels int32 [n], confidence [n,C-1] f32 or None)  (predict_mos.py:440-454)."""
+    logits = _req(logits, F32, "mos_labels")
+    n, Cc = logits.shape
+    labels = torch.empty(n, dtype=I32, device=logits.device)
+    conf = torch.empty((n, Cc - 1), dtype=F32, device=logits.device) if want_confidence else None
+    call("insmos_mos_labels", _p(logits), n, Cc, int(ignore_mask), _p(label_map), _p(labels), _p(conf), _stream())
+    return labels, conf

@@ -1,0 +1,141 @@
+"""Scan pipeline around InsMOSNet.forward: the steps immediately before and after the hot path.
+
+Mirrors what scripts/predict_mos.py does per sample on the host -- DemoDataset.__getitem__ (:114-159: pose transform in
+float64, timestamps, concatenation), `.cuda()` (:418), and the label step (:436-456: mask, softmax, argmax, label map,
+`.cpu().numpy()`) -- as: ONE pinned host->device copy of the raw scans on a copy stream, one staging kernel, the forward,
+one labelling kernel and two small asynchronous device->host copies into pinned buffers.  Two slots are in flight, so
+the copies of scan k+1 / k-1 overlap the forward of scan k; nothing here is a CPU fallback: the model and the staging
+kernels are CUDA only.
+"""
+import numpy as np
+import torch
+
+from insmos_b200 import ops
+
+DEFAULT_IGNORE = {0: True, 1: False, 2: False}            # config/semantic-kitti-mos.yaml:157-160
+DEFAULT_MAP_INV = {0: 0, 1: 9, 2: 251}                    # config/semantic-kitti-mos.yaml:152-155
+
+
+def scan_transforms(poses):
+    """inv(to_pose) @ from_pose per scan in float64, newest scan = target (predict_mos.py:132-136,162)."""
+    poses = np.asarray(poses, dtype=np.float64)
+    to_inv = np.linalg.inv(poses[-1])
+    return np.stack([to_inv @ p for p in poses])
+
+
+class _Slot:
+    def __init__(self, device, max_points, n_scans, n_class):
+        self.raw_host = torch.empty((max_points, 4), dtype=torch.float32).pin_memory()
+        self.aux_host = torch.empty(n_scans * 16 + n_scans, dtype=torch.float64).pin_memory()     # transforms | stamps
+        self.off_host = torch.empty(n_scans + 1, dtype=torch.int64).pin_memory()
+        self.raw_dev = torch.empty((max_points, 4), dtype=torch.float32, device=device)
+        self.aux_dev = torch.empty(n_scans * 16 + n_scans, dtype=torch.float64, device=device)
+        self.off_dev = torch.empty(n_scans + 1, dtype=torch.int64, device=device)
+        self.labels_host = torch.empty(max_points, dtype=torch.int32).pin_memory()
+        self.conf_host = torch.empty((max_points, n_class - 1), dtype=torch.float32).pin_memory()
+        self.copied = torch.cuda.Event()
+        self.done = torch.cuda.Event()
+        self.meta = None
+
+
+class ScanPipeline:
+    """submit(scans, poses) -> ticket; result(ticket) -> dict(labels int32 [Nc], confidence [Nc,C-1], boxes dict)."""
+
+    def __init__(self, model, dt_pred=0.1, n_scans=10, max_points=2_000_000, n_class=3, learning_ignore=None,
+                 learning_map_inv=None, transform=True, device=None, post_logits=None, out_rows=None):
+        self.model, self.dt, self.n_scans, self.transform = model, float(dt_pred), int(n_scans), bool(transform)
+        self.device = device if device is not None else next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("insmos_b200.ScanPipeline needs a CUDA model (no CPU fallback)")
+        ign = DEFAULT_IGNORE if learning_ignore is None else learning_ignore
+        inv = DEFAULT_MAP_INV if learning_map_inv is None else learning_map_inv
+        self.n_class = n_class
+        self.ignore_mask = sum(1 << int(k) for k, v in ign.items() if v)
+        self.label_map = torch.tensor([int(inv[k]) for k in range(n_class)], dtype=torch.int32, device=self.device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        # post_logits: optional hook applied to the per-point logits before labelling (multi-GPU: the NCCL gather of
+        # every rank's logits, insmos_b200.distributed.gather_logits); out_rows bounds the rows it may return
+        self.post_logits = post_logits
+        self.slots = [_Slot(self.device, max_points, self.n_scans, n_class) for _ in range(2)]
+        if out_rows is not None and out_rows > max_points:
+            for sl in self.slots:
+                sl.labels_host = torch.empty(out_rows, dtype=torch.int32).pin_memory()
+                sl.conf_host = torch.empty((out_rows, n_class - 1), dtype=torch.float32).pin_memory()
+        self.next_ticket = 0
+
+    def submit(self, scans, poses=None):
+        """scans: list of n_scans float32 arrays [Ni,4] (x,y,z,intensity), oldest first; poses: n_scans 4x4 float64.
+        The scans are packed into the slot's pinned buffer (one host memcpy) and handed to submit_packed."""
+        n = len(scans)
+        if n != self.n_scans:
+            raise ValueError("ScanPipeline: expected %d scans, got %d" % (self.n_scans, n))
+        slot = self._free_slot()
+        offs = np.zeros(n + 1, dtype=np.int64)
+        for i, s in enumerate(scans):
+            offs[i + 1] = offs[i] + s.shape[0]
+        total = int(offs[-1])
+        if total > slot.raw_host.shape[0]:
+            raise ValueError("ScanPipeline: %d points exceed max_points=%d" % (total, slot.raw_host.shape[0]))
+        raw = slot.raw_host.numpy()
+        for i, s in enumerate(scans):
+            raw[offs[i]:offs[i + 1]] = s[:, :4]
+        return self.submit_packed(slot.raw_host[:total], offs, poses)
+
+    def _free_slot(self):
+        slot = self.slots[self.next_ticket % 2]
+        if slot.meta is not None and not slot.meta.get("collected", False):
+            raise RuntimeError("ScanPipeline: collect result(%d) before submitting two more samples" % slot.meta["ticket"])
+        return slot
+
+    def submit_packed(self, raw_pinned, offsets, poses=None):
+        """raw_pinned: float32 [total,4] tensor in PINNED host memory holding the n_scans scans back to back (e.g. the
+        buffer the .bin files were read into), offsets: int64 [n_scans+1] row offsets.  No host copy: the H2D transfer
+        reads raw_pinned directly on the copy stream; the caller must not modify it until result(ticket) returned."""
+        n = self.n_scans
+        slot = self._free_slot()
+        offs = np.asarray(offsets, dtype=np.int64)
+        total = int(offs[-1])
+        if offs.shape[0] != n + 1 or raw_pinned.shape[0] < total or raw_pinned.dtype != torch.float32:
+            raise ValueError("ScanPipeline.submit_packed: need float32 [total,4] and %d offsets" % (n + 1))
+        if not raw_pinned.is_pinned():
+            raise ValueError("ScanPipeline.submit_packed: raw_pinned must live in pinned host memory (tensor.pin_memory())")
+        if total > slot.raw_dev.shape[0]:
+            raise ValueError("ScanPipeline: %d points exceed max_points=%d" % (total, slot.raw_dev.shape[0]))
+        aux = slot.aux_host.numpy()
+        use_T = self.transform and poses is not None
+        if use_T:
+            aux[:n * 16] = scan_transforms(poses).reshape(-1)
+        # t_i = round((i - n + 1) * dt, 3) as float32 (predict_mos.py:147-148,177)
+        aux[n * 16:] = np.array([np.float32(round((i - n + 1) * self.dt, 3)) for i in range(n)], dtype=np.float64)
+        slot.off_host.numpy()[:] = offs
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(slot.done)                   # the slot's previous forward has consumed raw_dev
+            slot.raw_dev[:total].copy_(raw_pinned[:total], non_blocking=True)
+            slot.aux_dev.copy_(slot.aux_host, non_blocking=True)
+            slot.off_dev.copy_(slot.off_host, non_blocking=True)
+            slot.copied.record(self.copy_stream)
+        cur.wait_event(slot.copied)
+        T = slot.aux_dev[:n * 16].view(n, 4, 4) if use_T else None
+        stamps = slot.aux_dev[n * 16:].to(torch.float32)
+        pts = ops.stage_scans(slot.raw_dev[:total], slot.off_dev, T, stamps)
+        with torch.no_grad():
+            boxes, _, logits = self.model.forward([{"meta": None, "past_point_clouds": pts, "batch_size_npast": n}], "test")
+        lg = logits[0] if self.post_logits is None else self.post_logits(logits[0])
+        labels, conf = ops.mos_labels(lg, self.ignore_mask, self.label_map)
+        nc = labels.shape[0]
+        slot.labels_host[:nc].copy_(labels, non_blocking=True)
+        slot.conf_host[:nc].copy_(conf, non_blocking=True)
+        slot.done.record(cur)
+        slot.meta = {"ticket": self.next_ticket, "nc": nc, "boxes": boxes[0][0], "total": total, "collected": False}
+        self.next_ticket += 1
+        return slot.meta["ticket"]
+
+    def result(self, ticket):
+        slot = self.slots[ticket % 2]
+        if slot.meta is None or slot.meta["ticket"] != ticket:
+            raise KeyError("ScanPipeline: ticket %d is not in flight" % ticket)
+        slot.done.synchronize()
+        nc = slot.meta["nc"]
+        slot.meta["collected"] = True
+        return {"labels": slot.labels_host[:nc].numpy(), "confidence": slot.conf_host[:nc].numpy(), "boxes": slot.meta["boxes"]}

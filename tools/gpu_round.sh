@@ -1,7 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-rm -f gpurun_out/summary.txt
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest(gpu) rc=$?" | tee -a gpurun_out/summary.txt
-tail -5 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --dump-launches gpurun_out/launch_dump.jsonl > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" | tee -a gpurun_out/summary.txt
-head -c 300 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,temperature.gpu,clocks_event_reasons.active --format=csv
+timeout 300 python -m pytest tests/test_staging.py -m gpu -q 2>&1 | tail -3
+for rep in 1 2; do
+timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench$rep.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+python -c "import json;d=json.load(open('gpurun_out/bench$rep.json'));print(d['value'],d['ms_per_step'],d['e2e']['value'],d['e2e']['ms_per_step'],d['clocks'])"; tail -3 gpurun_out/bench.err
+done
