@@ -219,6 +219,15 @@ def main():
                         out_rows=max_pts * world)
 
     def timed(e2e):
+        import gc
+        gc.collect()
+        gc.disable()                                   # no collector pauses inside the timed region (re-enabled below)
+        try:
+            return _timed(e2e)
+        finally:
+            gc.enable()
+
+    def _timed(e2e):
         with torch.no_grad():
             last = None
             if e2e:

@@ -6,6 +6,8 @@ Every function requires CUDA tensors; there is no CPU path.
 """
 import ctypes as C
 
+import os as _os
+
 import torch
 
 from . import _lib
@@ -268,15 +270,27 @@ class Rulebook:
         return trip[torch.argsort(key)]
 
 
+_TM_OVERRIDE = int(_os.environ.get("INSMOS_TM", "0"))
+
+
 def choose_tile_rows(n_out, K):
-    # enough tiles that every layer exposes thousands of independent warps (one warp per tile x channel group)
-    tm = 128 if n_out >= 300_000 else 64 if n_out >= 150_000 else 32 if n_out >= 75_000 else 16
+    """rows per rule-book tile.  Larger tiles fill the 16-pair chunks of the mma.sync kernel (a bucket holds ~0.2*TM
+    pairs in the 4D maps) but make the map build coarser; measured per map on B200 (C2 workload, rule book + its convs,
+    profiles/r01_tile_rows_ab.txt): 5x5x5x1 -> 64; 3^4 -> 128 from 50 k rows, 64 below; 3^3 -> 64 from 20 k rows, 16 below."""
+    if _TM_OVERRIDE in (16, 32, 64, 128) and K >= 27:
+        tm = _TM_OVERRIDE
+    elif K >= 100:
+        tm = 64
+    elif K >= 64:
+        tm = 128 if n_out >= 50_000 else 64
+    elif K >= 27:
+        tm = 64 if n_out >= 20_000 else 16
+    else:
+        tm = 128 if n_out >= 300_000 else 64 if n_out >= 150_000 else 32 if n_out >= 75_000 else 16
     while tm > 16 and tm * K >= 65536:
         tm //= 2
     return tm
 
-
-import os as _os
 
 USE_XBLOCK = _os.environ.get("INSMOS_XBLOCK", "1") != "0"
 # measured on B200 (C2 workload): 5-wide x runs 683 -> 404 us, 3-wide runs no gain (295 -> 277, 112 -> 124 us)
