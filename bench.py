@@ -299,16 +299,18 @@ def main():
     top = max((k for k in fam if fam[k]["bytes"] > 0), key=lambda k: fam[k]["ms"])
     ach = fam[top]["bytes"] / (fam[top]["ms"] * 1e-3) / 1e9
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    tp = os.path.join(ROOT, "profiles", "traffic.json")       # dram__bytes_read+write per kernel family over ONE forward (ncu, tools/gpu_profile.sh)
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(top)
+            traffic = json.load(open(tp)).get(top, {}).get("dram_bytes_per_forward")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": top, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                 "traffic": traffic, "peak_source": peak_src,
-                "definition": "sum of algorithmic bytes of this kernel's launches in one step / sum of their CUDA-event "
-                              "durations (2 instrumented steps after the timed region); launches per step: %d" % round(fam[top]["launches"]),
+                "definition": "sum of algorithmic bytes of this kernel family's launches in one step / sum of their CUDA-event "
+                              "durations (2 instrumented steps after the timed region); launches per step: %d; traffic = ncu "
+                              "dram__bytes_read.sum + dram__bytes_write.sum summed over the same launches of one forward "
+                              "(profiles/r01_fwd_v7_summary.txt)" % round(fam[top]["launches"]),
                 "alg_bytes_per_step": int(fam[top]["bytes"]), "ms_per_step": round(fam[top]["ms"], 4)}
     kernels = {k: {"ms_per_step": round(v["ms"], 4), "launch_calls": v["launches"],
                    "alg_GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["bytes"] and v["ms"] > 0 else None,

@@ -53,9 +53,22 @@ __device__ __forceinline__ uint64_t hash64(uint64_t k) {
     return (uint64_t)h;
 }
 
+// Home slot of a voxel key.  A SPATIALLY BLOCKED variant (the 4 x 4 x 2 voxels of a block share one hashed 32-slot region)
+// was measured on B200 and lost: the map builds went 1.33 -> 1.48 ms per forward -- the longer probe chains of the
+// clustered regions cost more than the better line reuse gains (kept behind INSMOS_BLOCKED_HASH for the record).
+__device__ __forceinline__ uint64_t home_slot(uint64_t key, uint64_t mask) {
+#ifdef INSMOS_BLOCKED_HASH
+    const uint64_t local = (key & 3ull) | (((key >> 16) & 3ull) << 2) | (((key >> 32) & 1ull) << 4);
+    const uint64_t block = key & ~(3ull | (3ull << 16) | (1ull << 32));
+    return ((hash64(block) << 5) | local) & mask;
+#else
+    return hash64(key) & mask;
+#endif
+}
+
 // insert (or find) key; returns slot index. Table load factor <= 0.5 guarantees termination.
 __device__ __forceinline__ int64_t table_insert(insmos_slot_t* table, uint64_t mask, uint64_t key) {
-    uint64_t slot = hash64(key) & mask;
+    uint64_t slot = home_slot(key, mask);
     while (true) {
         unsigned long long* kp = reinterpret_cast<unsigned long long*>(&table[slot].key);
         unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
@@ -70,7 +83,7 @@ __device__ __forceinline__ int64_t table_insert(insmos_slot_t* table, uint64_t m
 
 // read-only lookup; returns row id or -1. One 16-byte load per probe step.
 __device__ __forceinline__ int table_find_row(const insmos_slot_t* __restrict__ table, uint64_t mask, uint64_t key) {
-    uint64_t slot = hash64(key) & mask;
+    uint64_t slot = home_slot(key, mask);
     while (true) {
         const int4 v = __ldg(reinterpret_cast<const int4*>(&table[slot]));
         const uint64_t k = ((uint64_t)(uint32_t)v.y << 32) | (uint32_t)v.x;

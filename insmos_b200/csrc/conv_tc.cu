@@ -257,7 +257,7 @@ k_spconv_tc3(TcArgs p) {
 // ahead) -> gathered rows (one chunk ahead) -> split -> mma -> shared-memory accumulate.
 #define TC4_INVALID 0xffffffffu
 template <int NT, int KSC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)                        // <= 128 registers: two 8-warp blocks per SM (ncu: <2,6> had 134 -> 12.5 % warps active)
 k_spconv_tc4(TcArgs p) {
     constexpr int CW = NT * 8;
     extern __shared__ __align__(16) float sm[];
@@ -611,7 +611,8 @@ extern "C" int insmos_sparse_conv_fwd_tc(const float* in, int64_t n_in, int32_t 
     // per-bucket barriers cost more than the saved traffic: 48->32 K=81 240 -> 550 us)
     if (a.NT8 >= 8 && getenv("INSMOS_NO_BIG") == nullptr) return launch_tc_big(a, (cudaStream_t)stream);
     // two n-tiles per warp halve the redundant gathers; only when that still leaves thousands of warps
-    if (a.NT8 % 2 == 0 && a.n_tiles * (a.NT8 / 2) >= 4096) {
+    static const bool nt2_always = getenv("INSMOS_TC_NT1") == nullptr;    // several warps per tile provide the parallelism: two n-tiles per warp whenever possible (A/B: 1.725 -> 1.70 ms)
+    if (a.NT8 % 2 == 0 && (nt2_always || a.n_tiles * (a.NT8 / 2) >= 4096)) {
         a.groups = a.NT8 / 2;
         return dispatch_ks<2>(a, (cudaStream_t)stream);
     }

@@ -106,6 +106,25 @@ def test_sparse_conv_umma_strided_and_transposed(cuda):
     assert torch.allclose(ops.sparse_conv(ref.to(cuda), Wt.to(cuda), rbt, algo=4).cpu(), reft, rtol=UMMA_RTOL, atol=UMMA_ATOL)
 
 
+def test_sparse_conv_umma_tiny_and_ragged_inputs(cuda):
+    """fewer rows than one 128-row super-tile, a row count that is not a multiple of the tile, and an empty set."""
+    g = torch.Generator().manual_seed(2)
+    for n_pts in (1, 37, 129, 300):
+        xyz = torch.randint(-6, 6, (n_pts, 3), generator=g)
+        c = torch.cat([torch.zeros((n_pts, 1), dtype=torch.long), xyz, torch.zeros((n_pts, 1), dtype=torch.long)], 1).to(torch.int32)
+        cs, _ = ops.unique_coords(c.to(cuda))
+        cn = cs.coords.cpu().numpy()
+        maps = me.kernel_map(cn, cn, [3, 3, 3, 1], [1, 1, 1, 1])
+        rb = ops.build_rulebook(cs, cs, ops.spec_me_cube([3, 3, 3, 1], [1, 1, 1, 1]))
+        feats = torch.randn((len(cn), 40), generator=g)
+        W = torch.randn((27, 40, 32), generator=g) / 12.0
+        ref = me.conv(feats, W, maps, len(cn))
+        out = ops.sparse_conv(feats.to(cuda), W.to(cuda), rb, algo=4).cpu()
+        assert torch.allclose(out, ref, rtol=UMMA_RTOL, atol=UMMA_ATOL), (n_pts, (out - ref).abs().max())
+        out2 = ops.sparse_conv(feats.to(cuda), W.to(cuda), rb, algo=2).cpu()
+        assert torch.allclose(out2, ref, rtol=RTOL, atol=ATOL)
+
+
 def test_conv0_125_offsets_single_channel(cuda):
     cs, c, maps, rb = _setup(cuda, [5, 5, 5, 1])
     g = torch.Generator().manual_seed(3)
