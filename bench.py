@@ -187,6 +187,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"              # stdout carries exactly one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=device)
     from insmos_b200 import _lib
 
