@@ -287,7 +287,7 @@ extern "C" int insmos_boxes_to_voxel_units(const float* boxes7, const int32_t* l
 //   first = smallest voxel index inside the box; voxel j is marked iff it is inside AND
 //   (j == first OR j lies within +-extent (full extents, axis aligned) of voxel `first`).
 // Two passes, thread per voxel, boxes staged in shared memory in chunks.
-#define MB_CHUNK 256
+#define MB_CHUNK 64            // boxes per block: the chunks are a grid dimension (ncu: 13 % warps active with the chunk loop inside a thread)
 struct BoxS { float cx, cy, cz, ex, ey, ez, c, s; int label; };
 
 __device__ __forceinline__ void load_boxes(const float* __restrict__ b8, int nb, int b0, float mult, BoxS* sb) {
@@ -318,8 +318,8 @@ k_member_first(const int32_t* __restrict__ coords, int64_t n, const float* __res
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int x = 0, y = 0, z = 0;
     if (j < n) { const int32_t* p = coords + j * 4; z = p[1]; y = p[2]; x = p[3]; }
-    for (int b0 = 0; b0 < nb; b0 += MB_CHUNK) {
-        __syncthreads();
+    {
+        const int b0 = blockIdx.y * MB_CHUNK;
         load_boxes(b8, nb, b0, mult, sb);
         __syncthreads();
         const int m = min(MB_CHUNK, nb - b0);
@@ -337,8 +337,8 @@ k_member_mark(const int32_t* __restrict__ coords, int64_t n, const float* __rest
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int x = 0, y = 0, z = 0;
     if (j < n) { const int32_t* p = coords + j * 4; z = p[1]; y = p[2]; x = p[3]; }
-    for (int b0 = 0; b0 < nb; b0 += MB_CHUNK) {
-        __syncthreads();
+    {
+        const int b0 = blockIdx.y * MB_CHUNK;
         load_boxes(b8, nb, b0, mult, sb);
         for (int i = threadIdx.x; i < MB_CHUNK; i += blockDim.x) {
             const int b = b0 + i;
@@ -380,9 +380,10 @@ extern "C" int insmos_box_membership(const int32_t* coords, int64_t n, const flo
     k_fill_i32<<<(nb + 255) / 256, 256, 0, st>>>(first_hit, nb, INT_MAX);
     INSMOS_CHECK_LAUNCH("k_fill_i32");
     const unsigned nblk = (unsigned)ceil_div64(n, 256);
-    k_member_first<<<nblk, 256, 0, st>>>(coords, n, boxes8, nb, mult, first_hit);
+    const dim3 grid(nblk, (unsigned)((nb + MB_CHUNK - 1) / MB_CHUNK));
+    k_member_first<<<grid, 256, 0, st>>>(coords, n, boxes8, nb, mult, first_hit);
     INSMOS_CHECK_LAUNCH("k_member_first");
-    k_member_mark<<<nblk, 256, 0, st>>>(coords, n, boxes8, nb, mult, first_hit, out, out_stride);
+    k_member_mark<<<grid, 256, 0, st>>>(coords, n, boxes8, nb, mult, first_hit, out, out_stride);
     INSMOS_CHECK_LAUNCH("k_member_mark");
     return INSMOS_OK;
 }
