@@ -16,6 +16,7 @@
 //           1e-3) rules out plain TF32, so every product is done as 3xTF32 (hi*hi + hi*lo + lo*hi,
 //           fp32 accumulate), which is fp32-accurate to ~2^-22.
 #include "common.cuh"
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float apply_epilogue(float v, int c, int64_t row, int Cout, const insmos_epilogue_t& ep) {
@@ -401,6 +402,64 @@ static int launch_linear_g8(const float* in, const float* weight, float* out, in
     return INSMOS_OK;
 }
 
+// One thread per row (ncu of k_linear_g8: 70-88 % issue-slot utilisation, two instructions per MAC -- an LDS per FFMA --
+// plus 3 shuffles per output): the row arrives as float4 loads, the weights are read as broadcast LDS.128 (every lane of
+// a warp reads the same address), COUTP accumulators stay in registers, no shuffles.  Cin % 4 == 0.
+template <int COUTP>
+__global__ void __launch_bounds__(128)
+k_linear_row(const float* __restrict__ in, const float* __restrict__ W, float* __restrict__ out,
+             int64_t n, int Cin, int Cout, insmos_epilogue_t ep) {
+    extern __shared__ __align__(16) float sw[];                   // [Cin][COUTP]
+    for (int i = threadIdx.x; i < Cin * COUTP; i += blockDim.x) {
+        const int ci = i / COUTP, co = i - ci * COUTP;
+        sw[i] = co < Cout ? W[ci * Cout + co] : 0.0f;
+    }
+    __syncthreads();
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const float4* x = reinterpret_cast<const float4*>(in + row * Cin);
+    float acc[COUTP];
+#pragma unroll
+    for (int c = 0; c < COUTP; ++c) acc[c] = 0.0f;
+    for (int c4 = 0; c4 < Cin / 4; c4 += 2) {                      // two float4 in flight
+        const float4 v0 = __ldg(x + c4);
+        const float4 v1 = (c4 + 1 < Cin / 4) ? __ldg(x + c4 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int ci = c4 * 4 + u;
+            if (ci < Cin) {
+                const float4* w = reinterpret_cast<const float4*>(sw + ci * COUTP);
+#pragma unroll
+                for (int q = 0; q < COUTP / 4; ++q) {
+                    const float4 ww = w[q];
+                    acc[4 * q + 0] = __fmaf_rn(vv[u], ww.x, acc[4 * q + 0]);
+                    acc[4 * q + 1] = __fmaf_rn(vv[u], ww.y, acc[4 * q + 1]);
+                    acc[4 * q + 2] = __fmaf_rn(vv[u], ww.z, acc[4 * q + 2]);
+                    acc[4 * q + 3] = __fmaf_rn(vv[u], ww.w, acc[4 * q + 3]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < COUTP; ++c)
+        if (c < Cout) out[row * Cout + c] = apply_epilogue(acc[c], c, row, Cout, ep);
+}
+
+template <int COUTP>
+static int launch_linear_row(const float* in, const float* weight, float* out, int64_t n, int Cin, int Cout,
+                             const insmos_epilogue_t& ep, cudaStream_t st) {
+    const size_t smem = sizeof(float) * (size_t)Cin * COUTP;
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_linear_row<COUTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    k_linear_row<COUTP><<<(unsigned)ceil_div64(n, 128), 128, smem, st>>>(in, weight, out, n, Cin, Cout, ep);
+    INSMOS_CHECK_LAUNCH("k_linear_row");
+    return INSMOS_OK;
+}
+
 extern "C" int insmos_linear_fwd(const float* in, int64_t n, int32_t Cin, const float* weight, int32_t Cout,
                                  float* out, const insmos_epilogue_t* ep_in, void* stream) {
     if (!in || !weight || !out || Cin <= 0 || Cout <= 0 || n < 0) return INSMOS_ERR_INVALID_ARG;
@@ -408,6 +467,13 @@ extern "C" int insmos_linear_fwd(const float* in, int64_t n, int32_t Cin, const 
     if (ep_in) ep = *ep_in;
     if (ep.scale && !ep.shift) return INSMOS_ERR_INVALID_ARG;
     if (n == 0) return INSMOS_OK;
+    if (Cout <= 32 && (Cin & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (size_t)Cin * 32 * sizeof(float) <= 64 * 1024 &&
+        getenv("INSMOS_LINEAR_G8") == nullptr) {
+        if (Cout <= 4) return launch_linear_row<4>(in, weight, out, n, Cin, Cout, ep, (cudaStream_t)stream);
+        if (Cout <= 8) return launch_linear_row<8>(in, weight, out, n, Cin, Cout, ep, (cudaStream_t)stream);
+        if (Cout <= 16) return launch_linear_row<16>(in, weight, out, n, Cin, Cout, ep, (cudaStream_t)stream);
+        return launch_linear_row<32>(in, weight, out, n, Cin, Cout, ep, (cudaStream_t)stream);
+    }
     if (Cout <= 32 && (size_t)Cin * 33 * sizeof(float) <= 160 * 1024) {
         if (Cout <= 8) return launch_linear_g8<8>(in, weight, out, n, Cin, Cout, ep, (cudaStream_t)stream);
         if (Cout <= 16) return launch_linear_g8<16>(in, weight, out, n, Cin, Cout, ep, (cudaStream_t)stream);

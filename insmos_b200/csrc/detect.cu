@@ -179,7 +179,7 @@ k_nms_mask(const float* __restrict__ boxes, int n, float thresh, unsigned long l
 __global__ void __launch_bounds__(64)
 k_nms_sweep(const unsigned long long* __restrict__ mask, int n, int max_keep, int32_t* __restrict__ keep, int32_t* num_keep) {
     const int col_blocks = (n + 63) / 64;
-    __shared__ unsigned long long diag[64];
+    __shared__ unsigned long long diag2[2][64];                   // diagonal words of block blk (and blk+1, prefetched)
     __shared__ unsigned long long s_kept;
     __shared__ int s_num;
     const int tid = threadIdx.x;
@@ -188,10 +188,15 @@ k_nms_sweep(const unsigned long long* __restrict__ mask, int n, int max_keep, in
     __syncthreads();
     // per-thread removal words for columns tid + 64*w are kept in a small local array
     unsigned long long remv_w[4] = {0ull, 0ull, 0ull, 0ull};     // supports n <= 16384
+    if (tid < min(64, n)) diag2[0][tid] = mask[(int64_t)tid * col_blocks];
     for (int blk = 0; blk < col_blocks; ++blk) {
         const int base = blk * 64;
         const int cnt = min(64, n - base);
-        if (tid < cnt) diag[tid] = mask[(int64_t)(base + tid) * col_blocks + blk];
+        unsigned long long* diag = diag2[blk & 1];
+        // the next block's diagonal does not depend on this block's outcome: fetch it now, one L2 round trip off the chain
+        unsigned long long nd = 0ull;
+        const bool pf = (blk + 1 < col_blocks) && (base + 64 + tid < n);
+        if (pf) nd = mask[(int64_t)(base + 64 + tid) * col_blocks + blk + 1];
         // removal word of this block lives in thread (blk & 63), slot (blk >> 6)
         __shared__ unsigned long long s_r;
         if (tid == (blk & 63)) s_r = remv_w[blk >> 6];
@@ -210,6 +215,7 @@ k_nms_sweep(const unsigned long long* __restrict__ mask, int n, int max_keep, in
         }
         __syncthreads();
         if (s_num >= max_keep) break;
+        if (pf) diag2[(blk + 1) & 1][tid] = nd;
         unsigned long long kept = s_kept;
         while (kept) {
             // up to 8 kept rows per step: all loads are issued before any is consumed (one L2 round trip per batch
