@@ -44,6 +44,27 @@ def _arr(ctype, vals):
     return (ctype * len(vals))(*vals)
 
 
+class _ZeroPool:
+    """zero-initialised scratch handed out in slices: one fill kernel per `chunk` elements instead of one torch.zeros
+    (a fill launch + ~5 us of host time) per rule book / coordinate op -- 35 of them per forward.  A slice is used once
+    and never handed out again; the pool lives on the stream it was created on (the forward runs on one stream)."""
+
+    def __init__(self, dtype, chunk=4096):
+        self.dtype, self.chunk, self.state = dtype, chunk, {}
+
+    def take(self, n, device):
+        key = (device.type, device.index, torch._C._cuda_getCurrentRawStream(device.index if device.index is not None else torch._C._cuda_getDevice()))
+        buf, used = self.state.get(key, (None, 0))
+        if buf is None or used + n > self.chunk:
+            buf, used = torch.zeros(self.chunk, dtype=self.dtype, device=device), 0
+        self.state[key] = (buf, used + n)
+        return buf[used:used + n]
+
+
+_ZERO_I32 = _ZeroPool(torch.int32)
+_ZERO_I64 = _ZeroPool(torch.int64)
+
+
 def _read_counters(counters, what):
     c = counters.cpu().tolist()            # one small D2H read; the only sync of a coordinate op
     if c[_lib.CNT_ERR] & _lib.DEVERR_COORD_RANGE:
@@ -111,7 +132,7 @@ def voxelize4d(points, quant):
     coords = torch.empty((max(n, 1), 5), dtype=I32, device=dev)
     inverse = torch.empty(max(n, 1), dtype=I32, device=dev)
     cur = torch.empty(max(n, 1), dtype=I32, device=dev)
-    counters = torch.zeros(_lib.NUM_COUNTERS, dtype=I32, device=dev)
+    counters = _ZERO_I32.take(_lib.NUM_COUNTERS, dev)
     call("insmos_voxelize4d", _p(points), n, stride, _arr(C.c_float, [float(q) for q in quant]), _p(table), cap,
          _p(slot), _p(coords), _p(inverse), _p(cur), _p(counters), _p(_scan_scratch(n, dev)), _stream())
     c = _read_counters(counters, "voxelize4d")
@@ -129,7 +150,7 @@ def unique_coords(coords, q=None, lazy=False):
     slot = torch.empty(max(n, 1), dtype=I32, device=dev)
     out = torch.empty((max(n, 1), ncol), dtype=I32, device=dev)
     inverse = torch.empty(max(n, 1), dtype=I32, device=dev)
-    counters = torch.zeros(_lib.NUM_COUNTERS, dtype=I32, device=dev)
+    counters = _ZERO_I32.take(_lib.NUM_COUNTERS, dev)
     qa = None if q is None else _arr(C.c_int32, [int(v) for v in q])
     call("insmos_unique_coords", _p(coords), n, ncol, qa, _p(table), cap, _p(slot), _p(out), _p(inverse),
          _p(counters), _p(_scan_scratch(n, dev)), _stream())
@@ -153,7 +174,7 @@ def spconv_out_coords(in_set, ksize, stride, pad, out_shape, lazy=False):
         reach *= -(-int(k_) // int(s_))
     table, cap = _new_table(n * min(reach, K), dev)
     out = torch.empty((max(n * K, 1), 4), dtype=I32, device=dev)
-    counters = torch.zeros(_lib.NUM_COUNTERS, dtype=I32, device=dev)
+    counters = _ZERO_I32.take(_lib.NUM_COUNTERS, dev)
     scratch = torch.empty(lib.insmos_spconv_out_scratch_bytes(n, K), dtype=torch.uint8, device=dev)
     call("insmos_spconv_out_coords", _p(in_set.coords), n, _arr(C.c_int32, list(ksize)), _arr(C.c_int32, list(stride)),
          _arr(C.c_int32, list(pad)), _arr(C.c_int32, list(out_shape)), _p(table), cap, _p(out), _p(counters),
@@ -181,7 +202,7 @@ def voxelize3d(points, pc_range, vsize, grid, max_voxels, max_points, want_voxel
     mean = torch.empty((rows_cap, Cc), dtype=F32, device=dev)
     ids = torch.empty(max(n, 1), dtype=I32, device=dev)
     work = torch.empty(mv * (1 + max_points), dtype=I32, device=dev)
-    counters = torch.zeros(_lib.NUM_COUNTERS, dtype=I32, device=dev)
+    counters = _ZERO_I32.take(_lib.NUM_COUNTERS, dev)
     call("insmos_voxelize3d", _p(points), n, Cc, _arr(C.c_float, [float(v) for v in pc_range]),
          _arr(C.c_float, [float(v) for v in vsize]), _arr(C.c_int32, [int(v) for v in grid]), mv, int(max_points),
          _p(table), cap, _p(slot), _p(coords), _p(num), _p(voxels), _p(mean), _p(ids), _p(work), _p(counters),
@@ -328,7 +349,7 @@ def build_rulebook(out_set, in_set, spec, TM=None, parent=None, xstep=None):
     n_tiles = max((n_out + TM - 1) // TM, 1)
     seg = torch.empty(n_tiles * (K + 1), dtype=torch.int16, device=dev)
     entries = torch.empty(max(lib.insmos_rulebook_entries_capacity(max(n_out, 1), K, TM), 1), dtype=I32, device=dev)
-    pc = torch.zeros(1, dtype=torch.int64, device=dev)
+    pc = _ZERO_I64.take(1, dev)
     if in_set.n > (1 << _lib.ROW_BITS):
         raise RuntimeError("insmos_b200.build_rulebook: more than 2^25 input rows")
     use_xb = (USE_XBLOCK and parent is None and xstep is not None and spec.mode == 0 and spec.first_fastest == 1
