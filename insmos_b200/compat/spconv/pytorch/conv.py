@@ -51,14 +51,25 @@ class SparseConvolution(SparseModule):
                 b = 1 / math.sqrt(fan_in)
                 self.bias.uniform_(-b, b)
 
-    def kernel_major_weight(self):
-        """[K, Cin, Cout] view of the spconv-layout weight, cached until the parameter changes."""
+    def kernel_major_weight(self, cin=None):
+        """[K, Cin, Cout] view of the spconv-layout weight, cached until the parameter changes.  cin > in_channels gives
+        the same weight with zero rows appended: the fused graph pads odd channel counts (16+3 instance bits, 7 point
+        features) to a multiple of 8 so that the vectorised gather / tensor-core paths apply; zero inputs times zero
+        weights add exact zeros."""
         ver = (self.weight._version, self.weight.data_ptr())
         if self._wk is None or self._wk[0] != ver:
             with torch.no_grad():
                 wk = self.weight.reshape(self.out_channels, -1, self.in_channels).permute(1, 2, 0).contiguous()
-            self._wk = (ver, wk)
-        return self._wk[1]
+            self._wk = (ver, wk, {})
+        if cin is None or cin == self.in_channels:
+            return self._wk[1]
+        pad = self._wk[2].get(cin)
+        if pad is None:
+            wk = self._wk[1]
+            with torch.no_grad():
+                pad = torch.cat([wk, wk.new_zeros((wk.shape[0], cin - self.in_channels, wk.shape[2]))], 1).contiguous()
+            self._wk[2][cin] = pad
+        return pad
 
     def prefetch_indices(self, in_set, in_shape, indice_dict):
         """queue the output-coordinate kernel of a strided SparseConv3d ahead of its forward (row count read lazily,
@@ -100,7 +111,10 @@ class SparseConvolution(SparseModule):
                     x.indice_dict[self.indice_key] = data
             rb = data.forward_rulebook()
             out_set, out_shape = data.out_set, data.out_shape
-        f = ops.sparse_conv(x.features, self.kernel_major_weight(), rb, scale=scale, shift=shift, bias=self.bias,
+        cin = x.features.shape[1]
+        if cin < self.in_channels:
+            raise ValueError("SparseConvolution: %d input channels, layer expects %d" % (cin, self.in_channels))
+        f = ops.sparse_conv(x.features, self.kernel_major_weight(cin), rb, scale=scale, shift=shift, bias=self.bias,
                             residual=residual, relu=relu, algo=algo)
         return SparseConvTensor(f, out_set.coords, out_shape, x.batch_size, indice_dict=x.indice_dict,
                                 benchmark=x.benchmark, coordset=out_set)

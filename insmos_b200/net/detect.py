@@ -48,8 +48,14 @@ class InstanceBoxes:
         self.boxes8 = ops.boxes_to_voxel_units(b7, pred["pred_labels"].to(torch.int32).contiguous(), range_min, voxel_size,
                                                float(stride)) if self.nb else torch.zeros((0, 8), device=b7.device)
 
+    PAD = 8                                            # the bits occupy 8 columns (3 used): C + 8 stays a multiple of 8
+
     def concat_bits(self, features, indices, mult):
-        """cat([features, one-hot class membership], dim=1) for the voxels `indices` [n,4] (b,z,y,x)."""
+        """cat([features, one-hot class membership, zero padding], dim=1) for the voxels `indices` [n,4] (b,z,y,x).
+        The reference concatenates exactly num_class columns (spconv_unet.py:345-349); the fused graph appends 8 so that
+        the next convolution's channel count stays a multiple of 8 (its weight gets zero rows, see
+        SparseConvolution.kernel_major_weight) -- odd counts fall off the vectorised tensor-core paths."""
         n, c = features.shape
-        bits = ops.box_membership(indices, self.boxes8, float(mult), n_class=self.num_class)
+        bits = torch.zeros((n, self.PAD), dtype=torch.float32, device=features.device)
+        ops.box_membership(indices, self.boxes8, float(mult), out=bits, out_stride=self.PAD, col_offset=0, n_class=self.num_class)
         return ops.concat2(features, bits), bits

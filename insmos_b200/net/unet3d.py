@@ -135,6 +135,8 @@ class UNetV2(nn.Module):
 
     def forward(self, batch_dict, Model_mode):
         feats, coords = batch_dict["voxel_features"], batch_dict["voxel_coords"]
+        if feats.shape[1] % 8:                                             # 7 point features -> 8 (zero column, zero weight rows)
+            feats = ops.concat2(feats, feats.new_zeros((feats.shape[0], 8 - feats.shape[1] % 8)))
         x = spconv.SparseConvTensor(features=feats, indices=coords.int(), spatial_shape=self.sparse_shape, batch_size=1,
                                     coordset=batch_dict.get("_voxel_set"))
         # the output coordinates of every strided convolution are queued one level ahead of its forward: the host read
