@@ -510,12 +510,28 @@ __global__ void k_concat2(const float* __restrict__ a, int C1, const float* __re
     const IDX row = idx / C; const int c = (int)(idx - row * C);
     out[idx] = (c < C1) ? a[(size_t)row * C1 + c] : b[(size_t)row * C2 + (c - C1)];
 }
+// float4 version for channel counts that are multiples of 4 (all concatenations of the fused graph): a quarter of the
+// threads and index arithmetic (the scalar kernel ran at ~0.7 TB/s effective: 71 us for the 377 k x 16 concat)
+__global__ void k_concat2_v4(const float4* __restrict__ a, int Q1, const float4* __restrict__ b, int Q2, uint32_t total4,
+                             float4* __restrict__ out) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total4) return;
+    const uint32_t Q = (uint32_t)(Q1 + Q2);
+    const uint32_t row = idx / Q;
+    const int q = (int)(idx - row * Q);
+    out[idx] = (q < Q1) ? __ldg(a + (size_t)row * Q1 + q) : __ldg(b + (size_t)row * Q2 + (q - Q1));
+}
 extern "C" int insmos_concat2(const float* a, int32_t C1, const float* b, int32_t C2, int64_t n,
                               float* out, void* stream) {
     if (!a || !b || !out || C1 <= 0 || C2 <= 0 || n < 0) return INSMOS_ERR_INVALID_ARG;
     if (n == 0) return INSMOS_OK;
     const int64_t total = n * (C1 + C2);
-    if (total < (1ll << 31))
+    const bool aligned = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if ((C1 & 3) == 0 && (C2 & 3) == 0 && aligned && total / 4 < (1ll << 32))
+        k_concat2_v4<<<(unsigned)ceil_div64(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4*>(a), C1 / 4, reinterpret_cast<const float4*>(b), C2 / 4, (uint32_t)(total / 4),
+            reinterpret_cast<float4*>(out));
+    else if (total < (1ll << 31))
         k_concat2<uint32_t><<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(a, C1, b, C2, n, out);
     else
         k_concat2<unsigned long long><<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(a, C1, b, C2, n, out);
