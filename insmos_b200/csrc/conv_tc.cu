@@ -1,18 +1,22 @@
-// Sparse convolution, tensor-core path (3xTF32 on mma.sync m16n8k8), v3.
+// Sparse convolution, tensor-core path for the NARROW layers (3xTF32 on mma.sync m16n8k8).
 //
-// Work decomposition as in v2 (one independent warp per (tile of TM output rows, group of NT n-tiles); bucket by
-// bucket; pairs of one bucket packed 16 at a time into the M dimension; accumulators of the tile in shared memory;
-// weights pre-arranged in fragment order, see insmos_conv_prep_weights in conv.cu).  What changed comes from the
-// ncu source page of v2 (profiles/r01_conv_v2_sass_notes.md): ~190 executed instructions per 16-pair chunk, 3 of
-// them HMMA.  v3 removes the bloat:
-//   * the TF32 hi/lo split of the gathered activations is hi = x & 0xffffe000, lo = x - hi (2 instructions; the
+// Work decomposition: a unit = (tile of TM output rows, group of NT n-tiles); wpt warps share a unit (bucket k -> warp
+// k mod wpt, private partial accumulator tiles in shared memory, summed in the epilogue); the pairs of one rule-book
+// bucket are packed 16 at a time into the M dimension; weights pre-arranged in fragment order and pre-split into TF32
+// hi/lo (insmos_conv_prep_weights in conv.cu).
+//   k_spconv_tc4<NT,KSC>  default: per-warp chunk list + counted loop (Cin = 8*KSC compile-time)
+//   k_spconv_tc3<NT,KSC>  previous generation with a data-dependent bucket iterator; still the path for channel counts
+//                         that are not a multiple of 8 (KSC = 0: runtime k-step loop) and the A/B switch INSMOS_TC_V3
+//   k_spconv_tc_big<NT>   block-cooperative variant for >= 64 output channels when the tcgen05 kernel is not eligible
+// History of the measurements that shaped them: profiles/r01_conv_v2_sass_notes.md, profiles/r01_umma_notes.md section 4.
+// v3 notes (kept because tc3 is still compiled):
+//   * the TF32 hi/lo split of the gathered activations is hi = (x + 0x1000) & 0xffffe000, lo = x - hi (3 instructions; the
 //     tensor core ignores the low 13 mantissa bits of lo) instead of cvt.rna.tf32 (emulated, ~4 instr + NaN path);
 //   * channel counts that are multiples of 8 up to 48 are compile-time (KSC = Cin/8): no per-chunk 64-bit address
 //     arithmetic, fully unrolled k-steps;
 //   * the weight fragments of a bucket are loaded once per bucket and kept in registers across its chunks;
-//   * the next chunk's rule-book entries AND gathered feature rows are prefetched one full iteration ahead, so the
-//     two dependent global-load latencies overlap the current chunk's mma + shared-memory accumulate.
-// KSC == 0 is the generic path (any Cin, runtime k-step loop, 4 k-steps of loads in flight).
+//   * the next chunk's rule-book entries AND gathered feature rows are prefetched, so the two dependent global-load
+//     latencies overlap the current chunk's mma + shared-memory accumulate.
 #include "common.cuh"
 #include <stdlib.h>
 

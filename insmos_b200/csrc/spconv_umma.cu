@@ -638,47 +638,47 @@ extern "C" int insmos_conv_prep_weights_umma(const float* weight, int32_t K, int
 // launch configuration of the TS kernel (shared by the sparse and the dense-image entry points)
 static int launch_umma_ts(UtArgs& t, void* workspace, int64_t workspace_bytes, cudaStream_t stream) {
     const int Cout = t.Cout, K = t.K;
-    struct { int64_t n_tiles; int G; int cchunks; } a = {t.n_tiles, t.G, t.cchunks};
-        const int64_t st = ceil_div64(a.n_tiles, a.G);
-        t.n_pad = st * UM_BM;
-        // TMEM budget: S A-stages of 64 columns + nacc accumulators of Cout columns, power of two.  Cout <= 64 fits in 256
-        // columns with 2 stages, so two CTAs share an SM and overlap each other's prologue / epilogue; Cout = 128 takes all 512.
-        t.stages = Cout <= 64 ? 2 : 4;
-        if (const char* e = getenv("INSMOS_UMMA_STAGES")) { const int v = atoi(e); if (v == 2 || v == 4) t.stages = v; }
-        const int acc_budget = (t.stages == 2 ? 256 : 512) - t.stages * 64;
-        t.nacc = 4;
-        while (t.nacc > 1 && Cout * t.nacc > acc_budget) t.nacc /= 2;
-        if (const char* e = getenv("INSMOS_UMMA_NACC")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && Cout * v <= acc_budget) t.nacc = v; }
-        t.tmem_cols = 32;
-        while (t.tmem_cols < t.stages * 64 + Cout * t.nacc) t.tmem_cols <<= 1;
-        const size_t smem_ts = 1024 + (size_t)t.stages * 2 * Cout * 128 + sizeof(int) * ((size_t)K * UM_BM + K + 4) +
-                               8 * (2 * UT_STAGES + 1) + 8 + 16 + 2 * (size_t)a.G * (K + 1) + 16;
-        const int per_sm = (t.tmem_cols <= 256 && 2 * (smem_ts + 1024) <= 227 * 1024) ? 2 : 1;
-        // offsets split over CTAs while the layer cannot fill the machine, as long as every CTA keeps >= 8 chunks
-        int ksplit = (int)((148 * per_sm) / st);
-        if (ksplit > 4) ksplit = 4;
-        if (ksplit > (K * a.cchunks) / 8) ksplit = (K * a.cchunks) / 8;
-        if (ksplit < 1) ksplit = 1;
-        if (const char* e = getenv("INSMOS_UMMA_KSPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 4) ksplit = v; }
-        const int64_t need = 256 + st * 4 + (int64_t)ksplit * t.n_pad * Cout * 4;
-        if (ksplit > 1 && (!workspace || workspace_bytes < need)) ksplit = 1;
-        t.ksplit = ksplit;
-        t.counters = nullptr; t.partial = nullptr;
-        if (ksplit > 1) {
-            t.counters = reinterpret_cast<unsigned int*>(workspace);
-            t.partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + ((st * 4 + 255) / 256) * 256);
-            INSMOS_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)st * 4, stream));
+    const struct { int64_t n_tiles; int G; int cchunks; } a = {t.n_tiles, t.G, t.cchunks};
+    const int64_t st = ceil_div64(a.n_tiles, a.G);
+    t.n_pad = st * UM_BM;
+    // TMEM budget: S A-stages of 64 columns + nacc accumulators of Cout columns, power of two.  Cout <= 64 fits in 256
+    // columns with 2 stages, so two CTAs share an SM and overlap each other's prologue / epilogue; Cout = 128 takes all 512.
+    t.stages = Cout <= 64 ? 2 : 4;
+    if (const char* e = getenv("INSMOS_UMMA_STAGES")) { const int v = atoi(e); if (v == 2 || v == 4) t.stages = v; }
+    const int acc_budget = (t.stages == 2 ? 256 : 512) - t.stages * 64;
+    t.nacc = 4;
+    while (t.nacc > 1 && Cout * t.nacc > acc_budget) t.nacc /= 2;
+    if (const char* e = getenv("INSMOS_UMMA_NACC")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && Cout * v <= acc_budget) t.nacc = v; }
+    t.tmem_cols = 32;
+    while (t.tmem_cols < t.stages * 64 + Cout * t.nacc) t.tmem_cols <<= 1;
+    const size_t smem_ts = 1024 + (size_t)t.stages * 2 * Cout * 128 + sizeof(int) * ((size_t)K * UM_BM + K + 4) +
+                           8 * (2 * UT_STAGES + 1) + 8 + 16 + 2 * (size_t)a.G * (K + 1) + 16;
+    const int per_sm = (t.tmem_cols <= 256 && 2 * (smem_ts + 1024) <= 227 * 1024) ? 2 : 1;
+    // offsets split over CTAs while the layer cannot fill the machine, as long as every CTA keeps >= 8 chunks
+    int ksplit = (int)((148 * per_sm) / st);
+    if (ksplit > 4) ksplit = 4;
+    if (ksplit > (K * a.cchunks) / 8) ksplit = (K * a.cchunks) / 8;
+    if (ksplit < 1) ksplit = 1;
+    if (const char* e = getenv("INSMOS_UMMA_KSPLIT")) { const int v = atoi(e); if (v >= 1 && v <= 4) ksplit = v; }
+    const int64_t need = 256 + st * 4 + (int64_t)ksplit * t.n_pad * Cout * 4;
+    if (ksplit > 1 && (!workspace || workspace_bytes < need)) ksplit = 1;
+    t.ksplit = ksplit;
+    t.counters = nullptr; t.partial = nullptr;
+    if (ksplit > 1) {
+        t.counters = reinterpret_cast<unsigned int*>(workspace);
+        t.partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + ((st * 4 + 255) / 256) * 256);
+        INSMOS_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)st * 4, stream));
+    }
+    if (smem_ts <= 227 * 1024) {
+        static thread_local size_t configured_ts = 0;
+        if (smem_ts > configured_ts) {
+            INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_spconv_umma_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ts));
+            configured_ts = smem_ts;
         }
-        if (smem_ts <= 227 * 1024) {
-            static thread_local size_t configured_ts = 0;
-            if (smem_ts > configured_ts) {
-                INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_spconv_umma_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ts));
-                configured_ts = smem_ts;
-            }
-            k_spconv_umma_ts<<<(unsigned)(st * ksplit), UM_THREADS, smem_ts, stream>>>(t);
-            INSMOS_CHECK_LAUNCH("k_spconv_umma_ts");
-            return INSMOS_OK;
-        }
+        k_spconv_umma_ts<<<(unsigned)(st * ksplit), UM_THREADS, smem_ts, stream>>>(t);
+        INSMOS_CHECK_LAUNCH("k_spconv_umma_ts");
+        return INSMOS_OK;
+    }
     return INSMOS_ERR_UNSUPPORTED;
 }
 
