@@ -154,11 +154,19 @@ def profile_stop():
     return out
 
 
+_FN = {}             # name -> (bound ctypes function, kernels per call)
+
+
 def call(name, *args):
     global LAUNCHES, NEXT_META
-    LAUNCHES += KERNELS_PER_CALL.get(name, 1)
+    ent = _FN.get(name)
+    if ent is None:
+        ent = _FN[name] = (getattr(load(), name), KERNELS_PER_CALL.get(name, 1))
+    LAUNCHES += ent[1]
     if PROFILE is None:
-        check(getattr(load(), name)(*args), name)
+        rc = ent[0](*args)
+        if rc != OK:
+            check(rc, name)
         return
     import torch
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -24,12 +24,12 @@ def _stream():
     # torch.cuda.current_stream() costs ~16 us of Python per call (cProfile on the GPU host: 2.2 ms per forward over
     # 136 C-ABI calls); the raw getter returns the same cudaStream_t handle in well under a microsecond
     if _raw_stream is not None:
-        return C.c_void_p(_raw_stream(torch._C._cuda_getDevice()))
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return _raw_stream(torch._C._cuda_getDevice())           # plain int: ctypes converts it for the c_void_p argument
+    return torch.cuda.current_stream().cuda_stream
 
 
 def _p(t):
-    return C.c_void_p(0 if t is None else t.data_ptr())
+    return None if t is None else t.data_ptr()                   # int / None -> c_void_p by the prototypes in _lib.PROTOTYPES
 
 
 def _req(t, dtype, name):
