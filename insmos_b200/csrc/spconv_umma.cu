@@ -569,7 +569,7 @@ k_spconv_umma_ts(UtArgs p) {
                 const int ksteps = (cw + 7) >> 3;
                 // accumulator 0 takes the two small cross products (|a_lo*b_hi|, |a_hi*b_lo| ~ 2^-11 |a*b|), accumulators
                 // 1..nacc-1 take the a_hi*b_hi products round-robin: the tensor core truncates on every accumulate, so the
-                // drift is proportional to the number of adds into a LARGE accumulator (tools/umma_accuracy.py)
+                // drift is proportional to the number of adds into a LARGE accumulator (tests/accuracy_umma.py)
                 const uint32_t dsmall = tmem_base + (uint32_t)acc_col;
                 const uint32_t dbig = tmem_base + (uint32_t)(acc_col + (nacc > 1 ? 1 + acc : 0) * NB);
                 const bool big_first = (nacc > 1) ? (i < nacc - 1) : false;
