@@ -1,22 +1,27 @@
 #!/usr/bin/env python3
 """bench.py -- scans/sec of the InsMOS sparse-voxel forward path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 A step = one InsMOSNet.forward(batch, 'test') over one synthetic sample of BASELINE config C2:
-N=10 stacked scans x 120 000 points (HDL-64E-shaped rays over a synthetic street scene), voxel 0.1 m,
-random-init weights (seeded per state_dict key) with BatchNorm statistics calibrated on the input.
-  value        whole-job scans/s with inputs resident in HBM (CUDA events, max over ranks)
-  e2e          same metric through the public call with HOST buffers: pinned H2D of the points and D2H of
-               the per-point logits inside the timed region
+N=10 stacked scans x 120 000 points (HDL-64E-shaped rays over a synthetic street scene), voxel 0.1 m, seeded weights with
+the BatchNorm statistics of tests/golden/insmos_c2.npz -- the exact weights and first cloud the C2 parity tests
+(tests/test_gpu_c2_golden.py) check against the reference-code golden.
+  value        whole-job scans/s with inputs resident in HBM (CUDA events, max over ranks); the K-step region is repeated
+               until >= 2 s have been timed and the MEDIAN region is reported (min/max beside it)
+  e2e          same metric through the public call with HOST buffers: pinned H2D of the raw scans, staging kernel, forward,
+               label kernel and D2H of the labels inside the timed region (insmos_b200.pipeline.ScanPipeline)
   roofline     dominant C-ABI kernel family: sum of algorithmic bytes / sum of CUDA-event durations, vs measured HBM peak
-  cpu_baseline the oracle (port of the reference's ME-CPU / spconv algorithms, MKL) on the host cores, bounded sample
---impl reference: the CPU port timed alone (the reference itself cannot run here: MinkowskiEngine / spconv are
-un-vendored externals); rank 0 only.
-Multi-GPU: samples sharded one per GPU (weak scaling), one padded NCCL all_gather of the logits per step.
+  cpu_baseline the oracle (port of the reference's ME-CPU / spconv algorithms, torch MKL) on the host cores: ONE full-size C2
+               forward, no extrapolation
+--impl reference: the CPU port timed alone on the FULL C2 cloud (the reference itself cannot run here: MinkowskiEngine /
+spconv are un-vendored externals); as many steps as fit the time budget, reported truthfully; rank 0 only.
+--workload c4: BASELINE config 4 (300 k points per scan, voxel 0.05 m): rule-book build + gather/scatter sweep line.
+Multi-GPU: samples sharded one per GPU (weak scaling), one fixed-size NCCL all_gather of the logits per step, no host sync.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -26,13 +31,15 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 N_SCANS, N_ELEV, N_AZIM = 10, 64, 1875
 WORKLOAD = "C2: N=10 stacked scans x 120k pts (1.2M points), voxel 0.1 m, full InsMOSNet forward ('test' mode)"
-CPU_FULL_SCAN_NOTE = "full-size oracle forward measured once in the dev container: 128 s/scan on 8 cores"
+MIN_TIMED_S = 2.0                      # the K-step region is repeated until this much has been timed
+GATHER_PAD_ROWS = 122_880              # fixed block of the logits all_gather (>= points of one scan)
 
 
 def peaks():
@@ -43,6 +50,16 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def source_digest():
+    """sha256 over the CUDA sources: ties profiles/traffic.json (ncu DRAM bytes) to the build it was measured on."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "insmos_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler(threading.Thread):
@@ -80,26 +97,21 @@ def make_clouds(rank, count, n_azim=N_AZIM):
     return [synth.make_sequence(seed=100 * rank + i, n_scans=N_SCANS, n_elev=N_ELEV, n_azim=n_azim) for i in range(count)]
 
 
-def build_model(device, calib_pts):
+def golden_state_dict():
+    """the C2 golden's weights: seeded per key + the BatchNorm statistics the reference code calibrated on cloud seed 0."""
+    import golden_util
+    meta, shapes, sd, _, _ = golden_util.load("c2", with_points=False)
+    return sd
+
+
+def build_model(device, calib_pts=None):
     import insmos_b200
     insmos_b200.install()
     from models.models import InsMOSNet
     from insmos_b200.config import default_config
-    from insmos_b200 import synth_weights
     net = InsMOSNet(default_config())
-    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
-    sd = synth_weights.fill_state_dict(shapes)
-    sd["model.unet.center_head.conv_cls.bias"] = torch.zeros(3)      # detections are non-empty
-    net.load_state_dict(sd, strict=True)
-    net = net.to(device)
-    # BatchNorm calibration on the input: one pass with batch statistics written to the running buffers
-    bns = [m for m in net.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)]
-    for m in bns:
-        m.momentum = 1.0
-    net.train()
-    with torch.no_grad():
-        net.forward([{"meta": None, "past_point_clouds": calib_pts, "batch_size_npast": N_SCANS}], "test")
-    return net.eval()
+    net.load_state_dict(golden_state_dict(), strict=True)
+    return net.to(device).eval()
 
 
 def step(net, pts):
@@ -107,66 +119,107 @@ def step(net, pts):
     return logits[0], boxes[0][0]
 
 
-def gather_logits(logits, world):
-    """the one exchange step of the path: per-point MOS logits of every rank's sample to all ranks (padded)."""
-    from insmos_b200.distributed import gather_logits as g
-    parts = g(logits, world)
-    return torch.cat(parts, 0), [p.shape[0] for p in parts]
-
-
-def cpu_port_scans_per_sec(sd_cpu, budget_s, steps=1, warmup=0):
-    """time oracle/graph.py (CPU port) on a bounded sample: every n-th azimuth of the same scene; result scaled to
-    full-size scans/s by the point ratio (cost is linear in points to first order)."""
+def cpu_port_full(sd_cpu, budget_s, max_steps):
+    """time oracle/graph.py (CPU port) on the FULL C2 cloud (seed 0): at least one step, more while they fit the budget."""
     from oracle import graph
     # the port's hot loops are small MKL GEMMs + index_add; beyond ~16 threads they get slower (measured on the
     # 128-core GPU host: 128 threads -> 30x slower than 16), so "all the threads it can use" is capped at 16
     torch.set_num_threads(min(os.cpu_count() or 1, 16))
-    frac = min(max((budget_s / max(steps + warmup, 1) - 3.0) / 130.0, 1.0 / 64), 1.0 / 4)
-    n_azim = max(int(round(N_AZIM * frac)), 24)
-    pts = make_clouds(0, 1, n_azim=n_azim)[0]
-    for _ in range(warmup):
-        graph.forward(sd_cpu, pts)
-    t0 = time.perf_counter()
-    timing = {}
-    for _ in range(steps):
+    pts = make_clouds(0, 1)[0]
+    times, timing = [], {}
+    t_begin = time.perf_counter()
+    while len(times) < max(max_steps, 1):
+        t0 = time.perf_counter()
         graph.forward(sd_cpu, pts, timing)
-    dt = (time.perf_counter() - t0) / steps
-    ratio = n_azim / N_AZIM
-    return {"value": ratio / dt, "unit": "scans/s", "cores": torch.get_num_threads(), "host_cores": os.cpu_count(),
-            "kind": "port",
-            "sample": "%d scans x %d x %d rays (%.1f%% of the C2 points), %.2f s per sample step, scaled to full-size "
-                      "scans/s by the point ratio; BLAS = torch MKL; %s" % (N_SCANS, N_ELEV, n_azim, 100 * ratio, dt, CPU_FULL_SCAN_NOTE),
-            "sample_seconds_per_step": dt, "rulebook_s": timing.get("me_maps_s"), "me_conv_s": timing.get("me_conv_s")}
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin + times[-1] > budget_s:
+            break
+    dt = float(np.mean(times))
+    return {"value": 1.0 / dt, "unit": "scans/s", "cores": torch.get_num_threads(), "host_cores": os.cpu_count(), "kind": "port",
+            "sample": "the full C2 cloud (10 scans x 64 x 1875 rays = 1.2 M points, seed 0), %d forward(s) of oracle/graph.py, "
+                      "%.1f s each, no extrapolation; BLAS = torch MKL" % (len(times), dt),
+            "steps": len(times), "seconds_per_step": dt,
+            "rulebook_s": timing.get("me_maps_s"), "me_conv_s": timing.get("me_conv_s"), "motionnet_s": timing.get("motionnet_s"),
+            "unet_encoder_s": timing.get("unet_encoder_s"), "bev_s": timing.get("bev_s"), "decoder_s": timing.get("decoder_s")}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    import insmos_b200
-    insmos_b200.install()
-    from models.models import InsMOSNet
-    from insmos_b200.config import default_config
-    from insmos_b200 import synth_weights
-    shapes = {k: tuple(v.shape) for k, v in InsMOSNet(default_config()).state_dict().items()}
-    sd = synth_weights.fill_state_dict(shapes)
-    sd["model.unet.center_head.conv_cls.bias"] = torch.zeros(3)
-    cb = cpu_port_scans_per_sec(sd, budget_s=150.0, steps=args.steps, warmup=args.warmup)
+    sd = golden_state_dict()
+    cb = cpu_port_full(sd, budget_s=float(os.environ.get("INSMOS_REF_BUDGET_S", "170")), max_steps=args.steps)
     line = {"impl": "reference", "metric": "scans_per_sec", "value": cb["value"], "unit": "scans/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True,
+            "steps": cb["steps"], "warmup": 0, "requested": {"steps": args.steps, "warmup": args.warmup},
+            "ms_per_step": 1000.0 * cb["seconds_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "CPU port of the reference's MinkowskiEngine-CPU / spconv algorithms "
-                       "(oracle/graph.py); uncalibrated BatchNorm statistics (timing only)"},
+                       "(oracle/graph.py) on the full C2 cloud with the golden's weights; one full-size forward takes ~1 min, so "
+                       "the run times as many steps as fit ~3 min and reports that count (steps) with no warm-up"},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def run_c4(args, device):
+    """BASELINE config 4: 300 k points per scan x 10, voxel 0.05 m -- per-map build time / pairs and the gather-scatter
+    kernels' algorithmic GB/s (the 100 k-voxel cap makes the full model meaningless at this density)."""
+    from insmos_b200 import ops, synth, _lib
+    pts = torch.from_numpy(synth.make_sequence(seed=4, n_scans=10, n_elev=160, n_azim=1875)).to(device)
+    peak, peak_src = peaks()
+
+    def timed(fn, reps):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            r = fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / reps, r
+
+    reps = max(args.steps, 5)
+    rows = []
+    ms, (cs, inverse, cur) = timed(lambda: ops.voxelize4d(pts, [0.05, 0.05, 0.05, 0.1]), reps)
+    n_pts = pts.shape[0]
+    b = 20 * n_pts + 20 * cs.n + 8 * n_pts
+    rows.append({"op": "voxelize4d", "ms": round(ms, 4), "n_points": n_pts, "n_voxels": cs.n, "alg_GBps": round(b / ms / 1e6, 1)})
+    ms, (c2s, parent) = timed(lambda: ops.unique_coords(cs.coords, q=[2, 2, 2, 1]), reps)
+    rows.append({"op": "stride_coords 1->2", "ms": round(ms, 4), "n_out": c2s.n, "alg_GBps": round((20 * cs.n + 20 * c2s.n + 4 * cs.n) / ms / 1e6, 1)})
+    g = torch.Generator().manual_seed(0)
+    for name, out_set, in_set, ksize, ist, xs, chans in (
+            ("5x5x5x1 ts1", cs, cs, [5, 5, 5, 1], [1, 1, 1, 1], 1, [(1, 8)]),
+            ("3x3x3x3 ts1", cs, cs, [3, 3, 3, 3], [1, 1, 1, 1], 1, [(8, 8), (16, 8)]),
+            ("2x2x2x1 ts1->ts2", c2s, cs, [2, 2, 2, 1], [1, 1, 1, 1], None, [(8, 8)]),
+            ("3x3x3x3 ts2", c2s, c2s, [3, 3, 3, 3], [2, 2, 2, 1], 2, [(8, 16), (16, 16)])):
+        spec = ops.spec_me_cube(ksize, ist)
+        ms, rb = timed(lambda: ops.build_rulebook(out_set, in_set, spec, xstep=xs), reps)
+        P, K = rb.num_pairs, int(np.prod(ksize))
+        b = 4 * out_set.ncol * out_set.n + 8 * P
+        rows.append({"op": "rulebook " + name, "ms": round(ms, 4), "n_out": out_set.n, "K": K, "pairs": P,
+                     "alg_GBps": round(b / ms / 1e6, 1), "frac_of_peak": round(b / ms / 1e6 / peak, 4)})
+        for Cin, Cout in chans:
+            x = torch.randn((in_set.n, Cin), generator=g).to(device)
+            W = (torch.randn((K, Cin, Cout), generator=g) / np.sqrt(Cin * 8.0)).to(device)
+            ms, _ = timed(lambda: ops.sparse_conv(x, W, rb), reps)
+            b = 4 * (in_set.n * Cin + out_set.n * Cout) + 8 * P + 4 * K * Cin * Cout
+            rows.append({"op": "sparse_conv %s %d->%d" % (name, Cin, Cout), "ms": round(ms, 4), "pairs": P,
+                         "alg_GBps": round(b / ms / 1e6, 1), "frac_of_peak": round(b / ms / 1e6 / peak, 4),
+                         "gflops": round(2 * P * Cin * Cout / ms / 1e6, 1)})
+    print(json.dumps({"metric": "c4_sweep", "workload": "C4: N=10 x 300k pts (3.0 M points), voxel 0.05 m: rule-book build + "
+                      "gather/scatter sparse conv sweep", "peak_GBps": peak, "peak_source": peak_src, "reps": reps, "rows": rows,
+                      "gpu_launches": _lib.launch_count()}))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--min-timed-s", type=float, default=MIN_TIMED_S)
     ap.add_argument("--dump-launches", default=None, help="write the per-C-ABI-call profile of one step (JSON lines)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -177,13 +230,16 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU port)")
-    # every distinct input cloud is seen once before the timed region (first-touch sizes hit cudaMalloc in the caching
-    # allocator: measured 9.4 -> 11.4 ms/step when the 4th cloud first appeared inside the timed loop)
-    args.warmup = max(args.warmup, 4)
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
+    if args.workload == "c4":
+        run_c4(args, device)
+        return
+    # every distinct input cloud is seen once before the timed region (first-touch sizes hit cudaMalloc in the caching
+    # allocator: measured 9.4 -> 11.4 ms/step when the 4th cloud first appeared inside the timed loop)
+    warmup = max(args.warmup, 4)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -191,21 +247,23 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"              # stdout carries exactly one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=device)
     from insmos_b200 import _lib
+    from insmos_b200.distributed import gather_logits_padded
 
     n_clouds = 4
     host = [torch.from_numpy(c).pin_memory() for c in make_clouds(rank, n_clouds)]
     dev = [h.to(device) for h in host]
-    net = build_model(device, dev[0])
+    net = build_model(device)
+    gather_out = torch.empty((world, GATHER_PAD_ROWS + 1, 3), dtype=torch.float32, device=device) if world > 1 else None
 
     def one(i):
         logits, boxes = step(net, dev[i % n_clouds])
-        if world > 1:
-            logits, _ = gather_logits(logits, world)
+        if world > 1:                                   # the one exchange step: fixed-size all_gather, no host sync
+            gather_logits_padded(logits, world, GATHER_PAD_ROWS, out=gather_out)
         return logits
 
     # e2e: the public host-buffer path (insmos_b200.pipeline.ScanPipeline): raw scans [N_i,4] in host
-    # memory + poses -> pinned H2D -> staging kernel (pose transform, time stamps) -> forward -> (NCCL gather) -> label
-    # kernel -> D2H of labels + confidence.  Two samples in flight: the copies of one overlap the forward of the other.
+    # memory + poses -> pinned H2D -> staging kernel (pose transform, time stamps) -> forward -> label kernel -> D2H of
+    # this rank's labels + confidence (+ NCCL gather of the logits on the device).  Two samples in flight.
     from insmos_b200.pipeline import ScanPipeline
     host_scans = []                                    # per cloud: (pinned [total,4] raw scans back to back, int64 offsets)
     for h in host:
@@ -216,62 +274,69 @@ def main():
         host_scans.append((torch.from_numpy(np.ascontiguousarray(np.concatenate(parts, 0))).pin_memory(), offs))
     poses = [np.eye(4)] * N_SCANS                      # synthetic clouds are already in the newest frame: T = I (same kernel work)
     max_pts = max(int(h.shape[0]) for h in host) + 1024
-    pipe = ScanPipeline(net, dt_pred=0.1, n_scans=N_SCANS, max_points=max_pts,
-                        post_logits=(lambda lg: gather_logits(lg, world)[0]) if world > 1 else None,
-                        out_rows=max_pts * world)
+    pipe = ScanPipeline(net, dt_pred=0.1, n_scans=N_SCANS, max_points=max_pts, gather_world=world, gather_pad_rows=GATHER_PAD_ROWS)
+
+    def region(e2e):
+        """exactly args.steps steps between two events, barrier + synchronize on both sides; -> (ms max over ranks, out)"""
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        if e2e:
+            prev = None
+            for i in range(args.steps):
+                t = pipe.submit_packed(*host_scans[i % n_clouds], poses)
+                if prev is not None:
+                    last = pipe.result(prev)                     # read sample i-1 on the host while sample i runs
+                prev = t
+            last = pipe.result(prev)
+            out = torch.from_numpy(last["labels"])
+        else:
+            for i in range(args.steps):
+                out = one(i)
+        e.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([s.elapsed_time(e)], device=device)
+        if dist:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms.item()), out
 
     def timed(e2e):
         import gc
         gc.collect()
-        gc.disable()                                   # no collector pauses inside the timed region (re-enabled below)
+        gc.disable()                                   # no collector pauses inside the timed regions (re-enabled below)
         try:
-            return _timed(e2e)
+            with torch.no_grad():
+                for i in range(warmup):
+                    if e2e:
+                        pipe.result(pipe.submit_packed(*host_scans[i % n_clouds], poses))
+                    else:
+                        one(i)
+                launches0 = _lib.launch_count()
+                ms0, out = region(e2e)
+                launches = _lib.launch_count() - launches0
+                # repeat the K-step region until >= min_timed_s have been timed; every rank runs the same count
+                reps = int(min(max(np.ceil(args.min_timed_s * 1000.0 / max(ms0, 1e-3)), 1), 400))
+                if dist:
+                    t = torch.tensor([reps], device=device)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    reps = int(t.item())
+                regions = [ms0] + [region(e2e)[0] for _ in range(reps - 1)]
+            return regions, launches, out
         finally:
             gc.enable()
 
-    def _timed(e2e):
-        with torch.no_grad():
-            last = None
-            if e2e:
-                for i in range(args.warmup):
-                    pipe.result(pipe.submit_packed(*host_scans[i % n_clouds], poses))
-            else:
-                for i in range(args.warmup):
-                    one(i)
-            torch.cuda.synchronize()
-            if dist:
-                dist.barrier()
-            launches0 = _lib.LAUNCHES
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            if e2e:
-                prev = None
-                for i in range(args.steps):
-                    t = pipe.submit_packed(*host_scans[i % n_clouds], poses)
-                    if prev is not None:
-                        last = pipe.result(prev)                     # read sample i-1 on the host while sample i runs
-                    prev = t
-                last = pipe.result(prev)
-                out = torch.from_numpy(last["labels"])
-            else:
-                for i in range(args.steps):
-                    out = one(i)
-            e.record()
-            torch.cuda.synchronize()
-            ms = torch.tensor([s.elapsed_time(e)], device=device)
-            if dist:
-                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-                dist.barrier()
-        return float(ms.item()), _lib.LAUNCHES - launches0, out
-
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms, launches, out = timed(False)
+    regions, launches, out = timed(False)
     sampler.stop_flag = True
-    ms_e2e, _, out_host = timed(True)
+    regions_e2e, _, out_host = timed(True)
+    ms, ms_e2e = float(np.median(regions)), float(np.median(regions_e2e))
     value = world * args.steps / (ms / 1000.0)
     e2e_value = world * args.steps / (ms_e2e / 1000.0)
-    n_cur = int(out_host.shape[0] // world)
+    n_cur = int(out_host.shape[0])
 
     # ---- per-kernel-family breakdown: CUDA events around every C-ABI call, 2 instrumented steps after the timed region
     fam, step_ms_prof = {}, None
@@ -292,27 +357,28 @@ def main():
             f["flops"] += meta.get("flops", 0) / 2
     conv_launches = sorted(({"ms": round(t, 4), **{k: m[k] for k in ("K", "Cin", "Cout", "n_out", "pairs")},
                              "alg_GBps": round(m["bytes"] / (t * 1e-3) / 1e9, 1)}
-                            for name, t, m in prof[len(prof) // 2:] if m and "Cin" in m), key=lambda d: -d["ms"])[:16]
+                            for name, t, m in prof[:len(prof) // 2] if m and "Cin" in m), key=lambda d: -d["ms"])[:16]
     if args.dump_launches and rank == 0:
         with open(args.dump_launches, "w") as fh:
-            for name, t, m in prof[len(prof) // 2:]:
+            for name, t, m in prof[:len(prof) // 2]:
                 fh.write(json.dumps({"call": name, "ms": round(t, 4), **(m or {})}) + "\n")
     peak, peak_src = peaks()
     top = max((k for k in fam if fam[k]["bytes"] > 0), key=lambda k: fam[k]["ms"])
     ach = fam[top]["bytes"] / (fam[top]["ms"] * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")       # dram__bytes_read+write per kernel family over ONE forward (ncu, tools/gpu_profile.sh)
+    traffic, traffic_note = None, "no ncu DRAM capture of this build (profiles/traffic.json absent or made from other sources)"
+    tp = os.path.join(ROOT, "profiles", "traffic.json")       # dram__bytes_read+write per kernel family over ONE forward (ncu)
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(top, {}).get("dram_bytes_per_forward")
+            tj = json.load(open(tp))
+            if tj.get("_src_digest") == source_digest():
+                traffic = tj.get(top, {}).get("dram_bytes_per_forward")
+                traffic_note = "ncu dram__bytes_read.sum + dram__bytes_write.sum over this family's launches of one forward of THIS build (%s)" % tj.get("_from", "profiles/")
         except Exception:
-            traffic = None
+            pass
     roofline = {"bound": "hbm", "kernel": top, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                "traffic": traffic, "peak_source": peak_src,
+                "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                 "definition": "sum of algorithmic bytes of this kernel family's launches in one step / sum of their CUDA-event "
-                              "durations (2 instrumented steps after the timed region); launches per step: %d; traffic = ncu "
-                              "dram__bytes_read.sum + dram__bytes_write.sum summed over the same launches of one forward "
-                              "(profiles/r01_fwd_v7_summary.txt)" % round(fam[top]["launches"]),
+                              "durations (2 instrumented steps after the timed region); launches per step: %d" % round(fam[top]["launches"]),
                 "alg_bytes_per_step": int(fam[top]["bytes"]), "ms_per_step": round(fam[top]["ms"], 4)}
     kernels = {k: {"ms_per_step": round(v["ms"], 4), "launch_calls": v["launches"],
                    "alg_GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["bytes"] and v["ms"] > 0 else None,
@@ -323,21 +389,30 @@ def main():
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             sd_cpu = {k: v.detach().cpu() for k, v in net.state_dict().items()}
-            cpu = cpu_port_scans_per_sec(sd_cpu, budget_s=22.0)
+            cpu = cpu_port_full(sd_cpu, budget_s=0.0, max_steps=1)      # exactly one full-size forward (~1 min)
         line = {
             "metric": "scans_per_sec", "value": round(value, 3), "unit": "scans/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "warmup": warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "parallelism": "samples sharded 1 per GPU, NCCL all_gather of logits" if world > 1 else "single GPU",
+            "config": {"workload": WORKLOAD, "parallelism": "samples sharded 1 per GPU, one fixed-size NCCL all_gather of logits per step" if world > 1 else "single GPU",
                        "l2": "no explicit flush: each step streams > 126 MB (rule books + features) and inputs rotate over %d distinct clouds" % n_clouds,
-                       "arithmetic": "fp32; sparse-conv products on tensor cores as 3xTF32 (fp32-accurate); cuDNN TF32 off",
+                       "arithmetic": "fp32; sparse-conv products on tensor cores as 3xTF32 (fp32-accurate) or fp32 FFMA; cuDNN TF32 off",
+                       "weights": "tests/golden/insmos_c2.npz (the C2 parity golden's weights)",
                        "points_per_step": int(dev[0].shape[0]), "current_points": n_cur},
+            "timing": {"regions": len(regions), "steps_per_region": args.steps, "timed_s": round(sum(regions) / 1000.0, 3),
+                       "ms_per_step_median": round(ms / args.steps, 4), "ms_per_step_min": round(min(regions) / args.steps, 4),
+                       "ms_per_step_max": round(max(regions) / args.steps, 4),
+                       "note": "value = median K-step region; each region is exactly K steps between barrier+synchronize"},
             "e2e": {"value": round(e2e_value, 3), "unit": "scans/s", "ms_per_step": round(ms_e2e / args.steps, 4),
+                    "regions": len(regions_e2e), "ms_per_step_min": round(min(regions_e2e) / args.steps, 4),
+                    "ms_per_step_max": round(max(regions_e2e) / args.steps, 4),
                     "h2d_bytes_per_step": int(host[0].shape[0] * 16 + N_SCANS * 17 * 8 + (N_SCANS + 1) * 8),
-                    "d2h_bytes_per_step": int(n_cur * world * 12),
+                    "d2h_bytes_per_step": int(n_cur * 12),
                     "path": "insmos_b200.pipeline.ScanPipeline: raw scans + poses in pinned host memory -> H2D -> staging kernel -> "
-                            "forward -> label kernel -> D2H (labels int32 + confidence 2 x f32 per point); 2 samples in flight"},
-            "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline,
+                            "forward -> label kernel -> D2H of this rank's sample (labels int32 + confidence 2 x f32 per point); "
+                            "2 samples in flight; bytes are per rank"},
+            "gpu_launches": int(launches), "gpu_launches_note": "counted inside libinsmos_b200.so at every kernel launch site over the first K-step region (insmos_launch_count)",
+            "clocks": sampler.summary(), "roofline": roofline,
             "kernels": kernels, "slowest_sparse_convs": conv_launches, "profiled_step_ms": round(step_ms_prof, 3),
         }
         if cpu is not None:

@@ -99,6 +99,9 @@ typedef struct {
 
 const char* insmos_version(void);
 const char* insmos_last_error(void);          /* text of the last CUDA error seen by this thread */
+/* number of CUDA kernels this library has launched in the process so far (incremented at every launch site);
+ * bench.py reports the difference over its timed region as `gpu_launches`.  No reference counterpart. */
+uint64_t insmos_launch_count(void);
 int64_t insmos_hash_capacity(int64_t n);      /* power of two >= 2n (min 1024) */
 int64_t insmos_scan_scratch_bytes(int64_t n); /* scratch needed by ops that scan n elements */
 

@@ -36,6 +36,7 @@ _F = C.c_float
 PROTOTYPES = {
     "insmos_version": (C.c_char_p, []),
     "insmos_last_error": (C.c_char_p, []),
+    "insmos_launch_count": (C.c_uint64, []),
     "insmos_hash_capacity": (_I64, [_I64]),
     "insmos_scan_scratch_bytes": (_I64, [_I64]),
     "insmos_table_clear": (C.c_int, [_P, _I64, _P]),
@@ -88,7 +89,12 @@ PROTOTYPES = {
 }
 
 _lib = None
-LAUNCHES = 0          # number of C-ABI calls that launch kernels (bench.py reports it)
+LAUNCHES = 0          # kernels launched per the KERNELS_PER_CALL table (cross-check of the native counter)
+
+
+def launch_count():
+    """kernels launched by libinsmos_b200.so so far, counted inside the library at every launch site."""
+    return int(load().insmos_launch_count())
 
 
 def load():

@@ -184,11 +184,8 @@ extern "C" int insmos_conv2d_nhwc_tc(const float* in, int32_t H, int32_t W, int3
     if (Cin % BK != 0 || Cout % BN != 0) return INSMOS_ERR_UNSUPPORTED;
     ConvP p{in, weight, bias, out, H, W, Cin, Cout, mode, relu};
     constexpr size_t smem = sizeof(float) * 2 * (2 * BM * A_STRIDE + 2 * BK * B_STRIDE);
-    static thread_local bool configured = false;
-    if (!configured) {
-        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_conv_nhwc_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static thread_local insmos_smem_cfg_t configured;
+    INSMOS_CHECK_CUDA(insmos_ensure_smem(k_conv_nhwc_tc, smem, configured));
     dim3 grid((unsigned)((H * W + BM - 1) / BM), (unsigned)(Cout / BN), mode == 2 ? 4u : 1u);
     k_conv_nhwc_tc<<<grid, CONV_THREADS, smem, (cudaStream_t)stream>>>(p);
     INSMOS_CHECK_LAUNCH("k_conv_nhwc_tc");

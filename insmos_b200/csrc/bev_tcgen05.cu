@@ -225,11 +225,8 @@ extern "C" int insmos_conv2d_nhwc_tcgen05(const float* in, int32_t H, int32_t W,
     if (Cin % T5_BK != 0 || Cout % T5_BN != 0) return INSMOS_ERR_UNSUPPORTED;
     T5Args p{in, wimg, bias, out, H, W, Cin, Cout, mode, relu};
     constexpr size_t smem = 1024 + (size_t)T5_STAGES * T5_STAGE_BYTES + 8 * (2 * T5_STAGES + 1) + 16;
-    static thread_local bool configured = false;
-    if (!configured) {
-        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_conv_nhwc_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static thread_local insmos_smem_cfg_t configured;
+    INSMOS_CHECK_CUDA(insmos_ensure_smem(k_conv_nhwc_tcgen05, smem, configured));
     dim3 grid((unsigned)((H * W + T5_BM - 1) / T5_BM), (unsigned)(Cout / T5_BN), mode == 2 ? 4u : 1u);
     k_conv_nhwc_tcgen05<<<grid, T5_THREADS, smem, (cudaStream_t)stream>>>(p);
     INSMOS_CHECK_LAUNCH("k_conv_nhwc_tcgen05");

@@ -11,9 +11,12 @@
 #define INSMOS_ROW_MASK ((1u << INSMOS_ROW_BITS) - 1u)
 
 void insmos_set_last_error(const char* what, cudaError_t e);
+extern unsigned long long g_insmos_launches;      // kernels launched by this library (insmos_launch_count)
 
+// follows EVERY kernel launch of the library: counts it and turns a launch error into INSMOS_ERR_CUDA
 #define INSMOS_CHECK_LAUNCH(what)                                   \
     do {                                                            \
+        __atomic_fetch_add(&g_insmos_launches, 1ull, __ATOMIC_RELAXED); \
         cudaError_t _e = cudaGetLastError();                        \
         if (_e != cudaSuccess) {                                    \
             insmos_set_last_error(what, _e);                        \
@@ -31,6 +34,23 @@ void insmos_set_last_error(const char* what, cudaError_t e);
     } while (0)
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Opt-in to > 48 KB of dynamic shared memory.  cudaFuncSetAttribute is PER DEVICE, so the "already configured" cache of
+// every launcher is keyed by the current device (a process may drive several GPUs).
+struct insmos_smem_cfg_t { size_t v[16] = {0}; };
+template <class Kern>
+static inline cudaError_t insmos_ensure_smem(Kern kern, size_t smem, insmos_smem_cfg_t& cfg) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    size_t& have = cfg.v[dev & 15];
+    if (smem > have) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) have = smem;
+    }
+    return e;
+}
 
 // ---- 64-bit key packing: c0,c1,c2 16 bit (biased 32768), c3 8 bit (biased 128), batch 8 bit ----
 __device__ __forceinline__ bool coord_in_range(int b, int c0, int c1, int c2, int c3) {

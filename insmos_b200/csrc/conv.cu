@@ -238,11 +238,8 @@ static int launch_tc(const float* in, const void* wf, const uint16_t* seg, const
     const int groups = (NT8 + NT - 1) / NT;
     const size_t smem = sizeof(float) * (size_t)MMA_WARPS * TM * NT * 8 + sizeof(int) * (size_t)MMA_WARPS * (K + 1);
     if (smem > 220 * 1024) return INSMOS_ERR_UNSUPPORTED;
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_spconv_tc<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static thread_local insmos_smem_cfg_t configured;
+    INSMOS_CHECK_CUDA(insmos_ensure_smem(k_spconv_tc<NT>, smem, configured));
     const int64_t n_tiles = ceil_div64(n_out, TM);
     const int64_t warps = n_tiles * groups;
     k_spconv_tc<NT><<<(unsigned)ceil_div64(warps, MMA_WARPS), MMA_WARPS * 32, smem, st>>>(
@@ -291,11 +288,8 @@ extern "C" int insmos_sparse_conv_fwd(const float* in, int64_t n_in, int32_t Cin
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = sizeof(float) * (size_t)TM * Cout + sizeof(int) * (size_t)(K + 1);
     if (smem > 220 * 1024) return INSMOS_ERR_UNSUPPORTED;
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_spconv_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static thread_local insmos_smem_cfg_t configured;
+    INSMOS_CHECK_CUDA(insmos_ensure_smem(k_spconv_simt, smem, configured));
     k_spconv_simt<<<(unsigned)ceil_div64(n_out, TM), SIMT_THREADS, smem, st>>>(in, weight, seg, entries, out, n_out,
                                                                                Cin, Cout, K, TM, ep);
     INSMOS_CHECK_LAUNCH("k_spconv_simt");
@@ -387,11 +381,8 @@ template <int COUTP>
 static int launch_linear_g8(const float* in, const float* weight, float* out, int64_t n, int Cin, int Cout,
                             const insmos_epilogue_t& ep, cudaStream_t st) {
     const size_t smem = sizeof(float) * (size_t)Cin * (COUTP + 1);
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_linear_g8<COUTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static thread_local insmos_smem_cfg_t configured;
+    INSMOS_CHECK_CUDA(insmos_ensure_smem(k_linear_g8<COUTP>, smem, configured));
     int64_t blocks = ceil_div64(n, 32);
     // a large weight is staged once per block and the block strides over rows; a small one (<= 4 KB) is cheap to stage,
     // so every warp gets ONE group of 4 rows: these layers are latency bound (3 dependent memory round trips per row
@@ -450,11 +441,8 @@ template <int COUTP>
 static int launch_linear_row(const float* in, const float* weight, float* out, int64_t n, int Cin, int Cout,
                              const insmos_epilogue_t& ep, cudaStream_t st) {
     const size_t smem = sizeof(float) * (size_t)Cin * COUTP;
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_linear_row<COUTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static thread_local insmos_smem_cfg_t configured;
+    INSMOS_CHECK_CUDA(insmos_ensure_smem(k_linear_row<COUTP>, smem, configured));
     k_linear_row<COUTP><<<(unsigned)ceil_div64(n, 128), 128, smem, st>>>(in, weight, out, n, Cin, Cout, ep);
     INSMOS_CHECK_LAUNCH("k_linear_row");
     return INSMOS_OK;

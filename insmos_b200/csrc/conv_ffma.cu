@@ -197,11 +197,8 @@ k_ffma_block(FfArgs p, int G, int n_cb) {
 }
 
 template <class Kern>
-static int set_smem(Kern kern, size_t smem, size_t& configured) {
-    if (smem > 48 * 1024 && smem > configured) {
-        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+static int set_smem(Kern kern, size_t smem, insmos_smem_cfg_t& configured) {
+    INSMOS_CHECK_CUDA(insmos_ensure_smem(kern, smem, configured));
     return INSMOS_OK;
 }
 
@@ -209,7 +206,7 @@ template <int COT>
 static int launch_warp(const FfArgs& a, cudaStream_t st) {
     const size_t smem = sizeof(float) * (size_t)FW_WARPS * a.TM * COT + sizeof(int) * (size_t)FW_WARPS * (a.K + 1);
     if (smem > 220 * 1024) return INSMOS_ERR_UNSUPPORTED;
-    static thread_local size_t configured = 0;
+    static thread_local insmos_smem_cfg_t configured;
     int rc = set_smem(k_ffma_warp<COT>, smem, configured);
     if (rc) return rc;
     k_ffma_warp<COT><<<(unsigned)ceil_div64(a.n_tiles, FW_WARPS), FW_WARPS * 32, smem, st>>>(a);
@@ -223,7 +220,7 @@ static int launch_block(const FfArgs& a, cudaStream_t st) {
     const int n_cb = (a.Cout + COB - 1) / COB;
     const size_t smem = sizeof(float) * ((size_t)G * a.TM * COB + (size_t)a.Cin * COB) + sizeof(int) * ((size_t)G * (a.K + 1) + G + 1);
     if (smem > 220 * 1024) return INSMOS_ERR_UNSUPPORTED;
-    static thread_local size_t configured = 0;
+    static thread_local insmos_smem_cfg_t configured;
     int rc = set_smem(k_ffma_block<COB>, smem, configured);
     if (rc) return rc;
     k_ffma_block<COB><<<(unsigned)(ceil_div64(a.n_tiles, G) * n_cb), FB_WARPS * 32, smem, st>>>(a, G, n_cb);
@@ -298,11 +295,8 @@ template <int COUT>
 static int launch_cin1(const FfArgs& a, cudaStream_t st) {
     const size_t smem = sizeof(float) * ((size_t)a.K * a.TM + (size_t)a.K * COUT) + sizeof(int) * ((size_t)a.K + 1);
     if (smem > 200 * 1024) return INSMOS_ERR_UNSUPPORTED;
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_spconv_cin1<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static thread_local insmos_smem_cfg_t configured;
+    INSMOS_CHECK_CUDA(insmos_ensure_smem(k_spconv_cin1<COUT>, smem, configured));
     k_spconv_cin1<COUT><<<(unsigned)a.n_tiles, 128, smem, st>>>(a);
     INSMOS_CHECK_LAUNCH("k_spconv_cin1");
     return INSMOS_OK;

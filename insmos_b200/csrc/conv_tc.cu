@@ -507,11 +507,8 @@ static int launch_tc_big(const TcArgs& a, cudaStream_t st) {
     const size_t smem = sizeof(float) * (size_t)G * a.TM * NT * 8 + sizeof(uint4) * (size_t)NT * a.KS * 32 +
                         sizeof(int) * (size_t)G * (a.K + 1);
     if (smem > 220 * 1024) return INSMOS_ERR_UNSUPPORTED;
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_spconv_tc_big<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static thread_local insmos_smem_cfg_t configured;
+    INSMOS_CHECK_CUDA(insmos_ensure_smem(k_spconv_tc_big<NT>, smem, configured));
     const int64_t stiles = ceil_div64(a.n_tiles, G);
     k_spconv_tc_big<NT><<<(unsigned)(stiles * n_slices), BIG_WARPS * 32, smem, st>>>(a, G, n_slices);
     INSMOS_CHECK_LAUNCH("k_spconv_tc_big");
@@ -530,11 +527,8 @@ static int launch_tc3(TcArgs a, cudaStream_t st) {
     const int nwarps = wpt > TC_WARPS ? wpt : TC_WARPS;
     const size_t smem = sizeof(float) * (size_t)nwarps * a.TM * NT * 8 + sizeof(int) * (size_t)nwarps * (a.K + 1);
     if (smem > 220 * 1024) return INSMOS_ERR_UNSUPPORTED;
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_spconv_tc3<NT, KSC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static thread_local insmos_smem_cfg_t configured;
+    INSMOS_CHECK_CUDA(insmos_ensure_smem(k_spconv_tc3<NT, KSC>, smem, configured));
     k_spconv_tc3<NT, KSC><<<(unsigned)ceil_div64(units, nwarps / wpt), nwarps * 32, smem, st>>>(a);
     INSMOS_CHECK_LAUNCH("k_spconv_tc3");
     return INSMOS_OK;
@@ -560,11 +554,8 @@ static int launch_tc4(TcArgs a, cudaStream_t st) {
     const int nbk = (a.K + wpt - 1) / wpt;
     const size_t smem = sizeof(float) * (size_t)nwarps * a.TM * NT * 8 + sizeof(uint32_t) * (size_t)nwarps * nbk * (1 + a.TM / 16);
     if (smem > 220 * 1024) return launch_tc3<NT, KSC>(a, st);
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_spconv_tc4<NT, KSC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static thread_local insmos_smem_cfg_t configured;
+    INSMOS_CHECK_CUDA(insmos_ensure_smem(k_spconv_tc4<NT, KSC>, smem, configured));
     k_spconv_tc4<NT, KSC><<<(unsigned)ceil_div64(units, nwarps / wpt), nwarps * 32, smem, st>>>(a);
     INSMOS_CHECK_LAUNCH("k_spconv_tc4");
     return INSMOS_OK;

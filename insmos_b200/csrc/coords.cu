@@ -15,6 +15,8 @@ void insmos_set_last_error(const char* what, cudaError_t e) {
     snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, cudaGetErrorString(e));
 }
 extern "C" const char* insmos_last_error(void) { return g_last_error; }
+unsigned long long g_insmos_launches = 0ull;
+extern "C" uint64_t insmos_launch_count(void) { return __atomic_load_n(&g_insmos_launches, __ATOMIC_RELAXED); }
 extern "C" const char* insmos_version(void) { return "insmos_b200 0.1 (sm_100a)"; }
 
 extern "C" int64_t insmos_hash_capacity(int64_t n) {

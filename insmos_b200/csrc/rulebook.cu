@@ -320,11 +320,8 @@ static int rulebook_build_impl(const int32_t* out_coords, int64_t n_out,
     const size_t smem = sizeof(int) * (((size_t)TM * spec->K + 1) & ~(size_t)1) + sizeof(int64_t) * ((size_t)spec->K + TM) +
                         sizeof(int) * ((size_t)spec->K * 4 + (size_t)TM * 5 + spec->K + 1);
     if (smem > 220 * 1024) return INSMOS_ERR_UNSUPPORTED;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_rulebook_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static thread_local insmos_smem_cfg_t configured;
+    INSMOS_CHECK_CUDA(insmos_ensure_smem(k_rulebook_tiles, smem, configured));
     const int64_t n_tiles = ceil_div64(n_out, TM);
     k_rulebook_tiles<<<(unsigned)n_tiles, RB_THREADS, smem, (cudaStream_t)stream>>>(
         out_coords, n_out, in_table, (uint64_t)(in_cap - 1), *spec, TM, seg, entries, pair_count, parent,

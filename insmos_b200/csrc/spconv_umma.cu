@@ -670,11 +670,8 @@ static int launch_umma_ts(UtArgs& t, void* workspace, int64_t workspace_bytes, c
         INSMOS_CHECK_CUDA(cudaMemsetAsync(workspace, 0, (size_t)st * 4, stream));
     }
     if (smem_ts <= 227 * 1024) {
-        static thread_local size_t configured_ts = 0;
-        if (smem_ts > configured_ts) {
-            INSMOS_CHECK_CUDA(cudaFuncSetAttribute(k_spconv_umma_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ts));
-            configured_ts = smem_ts;
-        }
+        static thread_local insmos_smem_cfg_t configured_ts;
+        INSMOS_CHECK_CUDA(insmos_ensure_smem(k_spconv_umma_ts, smem_ts, configured_ts));
         k_spconv_umma_ts<<<(unsigned)(st * ksplit), UM_THREADS, smem_ts, stream>>>(t);
         INSMOS_CHECK_LAUNCH("k_spconv_umma_ts");
         return INSMOS_OK;
@@ -743,12 +740,9 @@ extern "C" int insmos_sparse_conv_fwd_umma(const float* in, int64_t n_in, int32_
     while (nacc > 1 && a.NB * nacc * ctas_per_sm > 512) nacc /= 2;
     if (const char* e = getenv("INSMOS_UMMA_NACC")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && a.NB * v <= 512) nacc = v; }
     a.nacc = nacc;
-    static thread_local size_t configured[2] = {0, 0};
+    static thread_local insmos_smem_cfg_t configured[2];
     auto kern = stages == 4 ? k_spconv_umma<4> : k_spconv_umma<2>;
-    if (smem > configured[stages == 4]) {
-        INSMOS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[stages == 4] = smem;
-    }
+    INSMOS_CHECK_CUDA(insmos_ensure_smem(kern, smem, configured[stages == 4]));
     kern<<<(unsigned)(stiles * a.nsplit), UM_THREADS, smem, (cudaStream_t)stream>>>(a);
     INSMOS_CHECK_LAUNCH("k_spconv_umma");
     return INSMOS_OK;

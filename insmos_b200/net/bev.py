@@ -121,7 +121,12 @@ class BaseBEVBackbone(nn.Module):
             data_dict["spatial_features_2d_nhwc"] = self.forward_nhwc(x, H, W)
             data_dict["spatial_features_2d"] = None
             return data_dict
-        x0 = data_dict["current_bev"]
+        x0 = data_dict.get("current_bev")
+        if x0 is None:
+            # eval mode produced only the channels-last map, but this configuration (strides != 1, several blocks,
+            # channel counts off the tensor-core tiles) is not covered by the fused path: rebuild NCHW for the torch modules
+            xn, H, W = data_dict["current_bev_nhwc"]
+            x0 = xn.view(H, W, -1).permute(2, 0, 1).unsqueeze(0).contiguous()
         x, ups = x0, []
         for i, blk in enumerate(self.blocks):
             x = blk(x)

@@ -1,5 +1,5 @@
 """InsMOS_Model / InsMOSNet mirrors (models/models.py:27-59,269-376): same constructor, state_dict keys
-and forward(batch_data, Model_mode) contract; inference modes only ('test', 'eval' without losses)."""
+and forward(batch_data, Model_mode) contract; the inference mode 'test' only ('train' / 'eval' raise)."""
 import numpy as np
 import torch
 import torch.nn as nn
@@ -94,9 +94,13 @@ class InsMOS_Model(nn.Module):
         self.use_motion_loss = M["USE_MOTION_LOSS"]
 
     def forward(self, list_batch_dict, Model_mode):
-        if Model_mode not in ("test", "eval"):
-            raise NotImplementedError("Model_mode %r: only the inference forward is implemented (SURVEY 8f N3)" % Model_mode)
-        boxes_out, recall_out, logits_out, gt_out = [], [], [], []
+        if Model_mode != "test":
+            # 'train' needs target assignment, losses and backward kernels; 'eval' returns the validation losses and the
+            # per-sample recall records of generate_recall_record (models/models.py:331-359), which depend on the same
+            # training-side code.  Returning NaN losses / empty recall dicts would let a reference validation_step log
+            # garbage silently, so both modes refuse.
+            raise NotImplementedError("Model_mode %r: only the inference forward ('test') is implemented (SURVEY 8f N3)" % Model_mode)
+        boxes_out, recall_out, logits_out = [], [], []
         for batch_dict in list_batch_dict:
             batch_dict = self.motion_encoder(batch_dict)
             if not self.use_motion_loss:
@@ -107,10 +111,6 @@ class InsMOS_Model(nn.Module):
             boxes_out.append(pred_dicts)
             recall_out.append(recall_dicts)
             logits_out.append(point_seg)
-            if Model_mode == "eval":
-                gt_out.append(batch_dict["past_labels"][-1])
-        if Model_mode == "eval":
-            return boxes_out, recall_out, gt_out, logits_out, float("nan"), float("nan")
         return boxes_out, recall_out, logits_out
 
 

@@ -35,6 +35,11 @@ def _p(t):
 def _req(t, dtype, name):
     if not t.is_cuda:
         raise RuntimeError("insmos_b200.%s: CUDA tensor required (no CPU fallback)" % name)
+    # the C ABI launches on the CURRENT device's current stream (_stream()): a tensor of another GPU would be read by the
+    # wrong device's kernels, so refuse loudly instead of launching there (callers: `with torch.cuda.device(t.device)`)
+    if t.device.index != torch._C._cuda_getDevice():
+        raise RuntimeError("insmos_b200.%s: tensor lives on cuda:%d but the current device is cuda:%d; wrap the call in "
+                           "`with torch.cuda.device(tensor.device):`" % (name, t.device.index, torch._C._cuda_getDevice()))
     if t.dtype != dtype:
         raise TypeError("insmos_b200.%s: expected %s, got %s" % (name, dtype, t.dtype))
     return t.contiguous()
@@ -273,27 +278,36 @@ class Rulebook:
             self._pairs = int(self.pair_count.item())
         return self._pairs
 
-    def to_coo(self):
-        """decode to sorted (k, in_row, out_row) int64 triples -- for tests / statistics only."""
+    def triples(self):
+        """decode on the device to (k, in_row, out_row) int64 tensors in storage order -- tests / statistics only."""
         K, TM = self.K, self.TM
         n_tiles = (self.n_out + TM - 1) // TM
-        seg = (self.seg.view(torch.int16).to(torch.int32) & 0xFFFF).view(n_tiles, K + 1).cpu()
-        ent = self.entries.view(n_tiles, TM * K).cpu()
+        dev = self.seg.device
+        seg = (self.seg.view(torch.int16).to(torch.int64) & 0xFFFF).view(n_tiles, K + 1)
+        pos = torch.arange(TM * K, device=dev, dtype=torch.int64)
         ks, ins, outs = [], [], []
-        for t in range(n_tiles):
-            tot = int(seg[t, K])
-            if tot == 0:
-                continue
-            e = ent[t, :tot].to(torch.int64) & 0xFFFFFFFF
-            counts = (seg[t, 1:] - seg[t, :-1]).to(torch.int64)
-            ks.append(torch.repeat_interleave(torch.arange(K, dtype=torch.int64), counts))
+        step = max(1, (1 << 24) // (TM * K))                                # bounded temporaries: ~16 M slots per pass
+        ent = self.entries[:n_tiles * TM * K].view(n_tiles, TM * K)
+        for t0 in range(0, n_tiles, step):
+            sg = seg[t0:t0 + step]
+            live = pos[None, :] < sg[:, K:K + 1]
+            ti, pi = torch.nonzero(live, as_tuple=True)
+            k = torch.searchsorted(sg[:, 1:].contiguous(), pos[None, :].expand(sg.shape[0], -1).contiguous(), right=True)[ti, pi]
+            e = ent[t0:t0 + step][ti, pi].to(torch.int64) & 0xFFFFFFFF
+            ks.append(k)
             ins.append(e & ((1 << _lib.ROW_BITS) - 1))
-            outs.append((e >> _lib.ROW_BITS) + t * TM)
+            outs.append((e >> _lib.ROW_BITS) + (ti + t0) * TM)
         if not ks:
-            return torch.zeros((0, 3), dtype=torch.int64)
-        trip = torch.stack([torch.cat(ks), torch.cat(ins), torch.cat(outs)], dim=1)
+            z = torch.zeros(0, dtype=torch.int64, device=dev)
+            return z, z, z
+        return torch.cat(ks), torch.cat(ins), torch.cat(outs)
+
+    def to_coo(self):
+        """decode to sorted (k, in_row, out_row) int64 triples on the host -- for tests / statistics only."""
+        k, i, o = self.triples()
+        trip = torch.stack([k, i, o], dim=1)
         key = (trip[:, 0] * (self.n_in + 1) + trip[:, 1]) * (self.n_out + 1) + trip[:, 2]
-        return trip[torch.argsort(key)]
+        return trip[torch.argsort(key)].cpu()
 
 
 _TM_OVERRIDE = int(_os.environ.get("INSMOS_TM", "0"))
@@ -381,6 +395,12 @@ def build_rulebook(out_set, in_set, spec, TM=None, parent=None, xstep=None):
 
 # ---- feature ops --------------------------------------------------------------------------------
 def _epilogue(scale=None, shift=None, bias=None, residual=None, relu=False):
+    """kernel epilogue: v*scale+shift, +bias, +residual, relu.  A conv bias followed by a fused BatchNorm means
+    BN(conv + bias) = acc*scale + (shift + bias*scale): the bias is folded into the shift here so that the kernels'
+    order (affine first, bias second) cannot apply it after the normalisation."""
+    if bias is not None and scale is not None:
+        shift = (shift if shift is not None else torch.zeros_like(scale)) + bias.reshape(-1) * scale
+        bias = None
     ep = Epilogue()
     keep = []
     for name, t in (("scale", scale), ("shift", shift), ("bias", bias), ("residual", residual)):

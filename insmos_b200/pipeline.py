@@ -42,7 +42,7 @@ class ScanPipeline:
     """submit(scans, poses) -> ticket; result(ticket) -> dict(labels int32 [Nc], confidence [Nc,C-1], boxes dict)."""
 
     def __init__(self, model, dt_pred=0.1, n_scans=10, max_points=2_000_000, n_class=3, learning_ignore=None,
-                 learning_map_inv=None, transform=True, device=None, post_logits=None, out_rows=None):
+                 learning_map_inv=None, transform=True, device=None, gather_world=1, gather_pad_rows=None, gather_group=None):
         self.model, self.dt, self.n_scans, self.transform = model, float(dt_pred), int(n_scans), bool(transform)
         self.device = device if device is not None else next(model.parameters()).device
         if self.device.type != "cuda":
@@ -53,14 +53,17 @@ class ScanPipeline:
         self.ignore_mask = sum(1 << int(k) for k, v in ign.items() if v)
         self.label_map = torch.tensor([int(inv[k]) for k in range(n_class)], dtype=torch.int32, device=self.device)
         self.copy_stream = torch.cuda.Stream(device=self.device)
-        # post_logits: optional hook applied to the per-point logits before labelling (multi-GPU: the NCCL gather of
-        # every rank's logits, insmos_b200.distributed.gather_logits); out_rows bounds the rows it may return
-        self.post_logits = post_logits
+        # multi-GPU: every rank labels and returns ITS OWN sample; the one exchange step -- the gather of the
+        # per-point logits of all ranks -- is a single fixed-size NCCL all_gather queued behind the forward with no host
+        # synchronisation (insmos_b200.distributed.gather_logits_padded); the gathered block stays on the device
+        # (result()["gathered"]) for whoever consumes the whole batch.
+        self.gather_world, self.gather_group = int(gather_world), gather_group
+        self.gather_pad_rows = int(gather_pad_rows) if gather_pad_rows else max_points // max(self.n_scans, 1) + 4096
         self.slots = [_Slot(self.device, max_points, self.n_scans, n_class) for _ in range(2)]
-        if out_rows is not None and out_rows > max_points:
+        if self.gather_world > 1:
             for sl in self.slots:
-                sl.labels_host = torch.empty(out_rows, dtype=torch.int32).pin_memory()
-                sl.conf_host = torch.empty((out_rows, n_class - 1), dtype=torch.float32).pin_memory()
+                sl.gather_buf = torch.empty((self.gather_world, self.gather_pad_rows + 1, n_class), dtype=torch.float32,
+                                            device=self.device)
         self.next_ticket = 0
 
     def submit(self, scans, poses=None):
@@ -91,6 +94,10 @@ class ScanPipeline:
         """raw_pinned: float32 [total,4] tensor in PINNED host memory holding the n_scans scans back to back (e.g. the
         buffer the .bin files were read into), offsets: int64 [n_scans+1] row offsets.  No host copy: the H2D transfer
         reads raw_pinned directly on the copy stream; the caller must not modify it until result(ticket) returned."""
+        with torch.cuda.device(self.device):           # the C ABI launches on the current device's current stream
+            return self._submit_packed(raw_pinned, offsets, poses)
+
+    def _submit_packed(self, raw_pinned, offsets, poses):
         n = self.n_scans
         slot = self._free_slot()
         offs = np.asarray(offsets, dtype=np.int64)
@@ -121,13 +128,18 @@ class ScanPipeline:
         pts = ops.stage_scans(slot.raw_dev[:total], slot.off_dev, T, stamps)
         with torch.no_grad():
             boxes, _, logits = self.model.forward([{"meta": None, "past_point_clouds": pts, "batch_size_npast": n}], "test")
-        lg = logits[0] if self.post_logits is None else self.post_logits(logits[0])
-        labels, conf = ops.mos_labels(lg, self.ignore_mask, self.label_map)
+        labels, conf = ops.mos_labels(logits[0], self.ignore_mask, self.label_map)
         nc = labels.shape[0]
         slot.labels_host[:nc].copy_(labels, non_blocking=True)
         slot.conf_host[:nc].copy_(conf, non_blocking=True)
+        gathered = None
+        if self.gather_world > 1:
+            from insmos_b200.distributed import gather_logits_padded
+            gathered = gather_logits_padded(logits[0], self.gather_world, self.gather_pad_rows, group=self.gather_group,
+                                            out=slot.gather_buf)
         slot.done.record(cur)
-        slot.meta = {"ticket": self.next_ticket, "nc": nc, "boxes": boxes[0][0], "total": total, "collected": False}
+        slot.meta = {"ticket": self.next_ticket, "nc": nc, "boxes": boxes[0][0], "total": total, "collected": False,
+                     "gathered": gathered}
         self.next_ticket += 1
         return slot.meta["ticket"]
 
@@ -138,4 +150,5 @@ class ScanPipeline:
         slot.done.synchronize()
         nc = slot.meta["nc"]
         slot.meta["collected"] = True
-        return {"labels": slot.labels_host[:nc].numpy(), "confidence": slot.conf_host[:nc].numpy(), "boxes": slot.meta["boxes"]}
+        return {"labels": slot.labels_host[:nc].numpy(), "confidence": slot.conf_host[:nc].numpy(), "boxes": slot.meta["boxes"],
+                "gathered": slot.meta["gathered"]}

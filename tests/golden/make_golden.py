@@ -80,7 +80,9 @@ def run_case(net, pts, cls_bias):
     inter = {}
     unet = net.model.unet
     hook = unet.center_head.register_forward_hook(lambda mod, inp, out: inter.update(
-        n_cand=int((torch.sigmoid(out["batch_cls_preds"]).max(-1)[0] >= 0.1).sum())))
+        n_cand=int((torch.sigmoid(out["batch_cls_preds"]).max(-1)[0] >= 0.1).sum()),
+        all_scores=torch.sigmoid(out["batch_cls_preds"][0]).max(-1)[0].numpy().copy(),
+        all_boxes=out["batch_box_preds"][0].numpy().copy()))
     b = batch()
     with torch.no_grad():
         boxes, recall, logits = net.forward(b, "test")
@@ -92,7 +94,7 @@ def run_case(net, pts, cls_bias):
         "pred_scores": boxes[0][0]["pred_scores"].numpy(), "pred_labels": boxes[0][0]["pred_labels"].numpy(),
         "current_point": d["current_point"].numpy(), "voxel_coords": d["voxel_coords"].numpy().astype(np.int32),
         "voxel_features": d["voxel_features"].numpy(), "pc_voxel_id": d["pc_voxel_id"].numpy(),
-        "n_cand": np.int64(inter["n_cand"]),
+        "n_cand": np.int64(inter["n_cand"]), "all_scores": inter["all_scores"], "all_boxes": inter["all_boxes"],
     }
 
 

@@ -15,8 +15,11 @@ def _worker(rank, world, port, ret):
         mine = D.shard_samples(5, rank, world)
         g = torch.Generator().manual_seed(rank)
         logits = torch.randn((1000 + 137 * rank, 3), generator=g)
-        parts = D.gather_logits(logits, world)
+        parts = D.gather_logits(logits, world, pad_rows=2048)
         ok = len(parts) == world
+        g = D.gather_logits_padded(logits, world, 2048)                       # counts travel in the payload, no size exchange
+        ok = ok and g.counts() == [1000 + 137 * r for r in range(world)] and tuple(g.buf.shape) == (world, 2049, 3)
+        ok = ok and bool((g.buf[rank, 1000 + 137 * rank:2048] == 0).all())
         for r in range(world):
             exp = torch.randn((1000 + 137 * r, 3), generator=torch.Generator().manual_seed(r))
             ok = ok and torch.equal(parts[r], exp)

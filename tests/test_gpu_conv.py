@@ -195,3 +195,21 @@ def test_dense_scatter_and_current_points(cuda):
     vf = torch.randn((50, 3), generator=g)
     out = ops.build_current_points(pts.to(cuda), cur.to(cuda), inv.to(cuda), vf.to(cuda), 3).cpu()
     assert torch.equal(out, torch.hstack([pts[cur.long(), :4], vf[inv[cur.long()].long()]]))
+
+
+@pytest.mark.parametrize("algo", [1, 2, 3, 4])
+def test_conv_bias_is_applied_before_the_fused_batchnorm(cuda, algo):
+    """a layer with bias=True followed by a fused BN computes BN(conv + bias) = (acc + bias) * scale + shift (ADVICE r01:
+    the kernels' epilogue order would otherwise add the bias after the normalisation)."""
+    cs, c, maps, rb = _setup(cuda, [3, 3, 3, 1])
+    g = torch.Generator().manual_seed(5)
+    Cin = Cout = 32
+    feats = torch.randn((len(c), Cin), generator=g)
+    W = torch.randn((27, Cin, Cout), generator=g) / 20.0
+    scale, shift, bias = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g), torch.randn(Cout, generator=g)
+    ref = torch.relu((me.conv(feats, W, maps, len(c)) + bias) * scale + shift)
+    out = ops.sparse_conv(feats.to(cuda), W.to(cuda), rb, scale=scale.to(cuda), shift=shift.to(cuda), bias=bias.to(cuda),
+                          relu=True, algo=algo).cpu()
+    assert torch.allclose(out, ref, rtol=UMMA_RTOL, atol=UMMA_ATOL), (out - ref).abs().max()
+    lin = ops.linear(feats.to(cuda), W[0].to(cuda), scale=scale.to(cuda), shift=shift.to(cuda), bias=bias.to(cuda)).cpu()
+    assert torch.allclose(lin, (feats @ W[0] + bias) * scale + shift, rtol=RTOL, atol=ATOL)
