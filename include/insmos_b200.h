@@ -205,6 +205,19 @@ int insmos_sparse_conv_fwd_ffma(const float* in, int64_t n_in, int32_t Cin,
                                 float* out, int64_t n_out,
                                 const insmos_epilogue_t* ep, void* stream);
 
+/* Exact-fp32 block-cooperative path of the same convolution for the NARROW layers (conv_fma.cu): a block owns a
+ * super-tile of rule-book tiles with its accumulators in shared memory, the kernel offsets are phases with W[k] staged
+ * once per block (cp.async, double buffered), lane = (pair, output-channel group), FFMA from registers x broadcast
+ * shared-memory weights.  Replaces MinkowskiConvolution / SubMConv3d forward for Cin % 8 == 0, Cout in {8,16,32}
+ * (minkunet.py:139-181, spconv_unet.py:284-406); insmos_sparse_conv_fma_supported tells; other shapes return
+ * INSMOS_ERR_UNSUPPORTED.  weight is the plain [K,Cin,Cout] fp32 tensor. */
+int insmos_sparse_conv_fma_supported(int32_t K, int32_t Cin, int32_t Cout);
+int insmos_sparse_conv_fwd_fma(const float* in, int64_t n_in, int32_t Cin,
+                               const float* weight, int32_t K, int32_t Cout,
+                               const uint16_t* seg, const uint32_t* entries, int32_t TM,
+                               float* out, int64_t n_out,
+                               const insmos_epilogue_t* ep, void* stream);
+
 /* Tensor-core path of the same convolution (3xTF32 on mma.sync m16n8k8, fp32 accumulate, fp32-accurate).
  * The weights are first rearranged ONCE per layer into tensor-core fragment order, pre-split into TF32 hi/lo
  * (wfrag: insmos_conv_wfrag_elems(K,Cin,Cout) 32-bit words, 16-byte aligned); the convolution then takes wfrag. */

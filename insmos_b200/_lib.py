@@ -57,6 +57,9 @@ PROTOTYPES = {
                                          C.POINTER(Epilogue), _I32, _P]),
     "insmos_sparse_conv_fwd_ffma": (C.c_int, [_P, _I64, _I32, _P, _I32, _I32, _P, _P, _I32, _P, _I64,
                                               C.POINTER(Epilogue), _P]),
+    "insmos_sparse_conv_fma_supported": (C.c_int, [_I32, _I32, _I32]),
+    "insmos_sparse_conv_fwd_fma": (C.c_int, [_P, _I64, _I32, _P, _I32, _I32, _P, _P, _I32, _P, _I64,
+                                             C.POINTER(Epilogue), _P]),
     "insmos_conv_wfrag_elems": (_I64, [_I32, _I32, _I32]),
     "insmos_conv_prep_weights": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
     "insmos_sparse_conv_fwd_tc": (C.c_int, [_P, _I64, _I32, _P, _I32, _I32, _P, _P, _I32, _P, _I64,
@@ -126,7 +129,7 @@ def check(rc, what):
 # kernels launched per C-ABI call (memsets not counted) -- used for bench.py's gpu_launches claim
 KERNELS_PER_CALL = {
     "insmos_table_clear": 1, "insmos_voxelize4d": 5, "insmos_unique_coords": 5, "insmos_spconv_out_coords": 4,
-    "insmos_voxelize3d": 8, "insmos_rulebook_build": 1, "insmos_sparse_conv_fwd": 1, "insmos_sparse_conv_fwd_tc": 1, "insmos_sparse_conv_fwd_ffma": 1, "insmos_conv_prep_weights": 1,
+    "insmos_voxelize3d": 8, "insmos_rulebook_build": 1, "insmos_sparse_conv_fwd": 1, "insmos_sparse_conv_fwd_tc": 1, "insmos_sparse_conv_fwd_ffma": 1, "insmos_sparse_conv_fwd_fma": 1, "insmos_conv_prep_weights": 1,
     "insmos_linear_fwd": 1,
     "insmos_affine_act": 1, "insmos_concat2": 1, "insmos_pairsum_add": 1, "insmos_gather_rows": 1,
     "insmos_segment_mean": 2, "insmos_build_current_points": 1, "insmos_dense_scatter": 1, "insmos_center_decode": 1,

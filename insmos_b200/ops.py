@@ -417,15 +417,21 @@ def _epilogue(scale=None, shift=None, bias=None, residual=None, relu=False):
 import os as _os
 
 # sparse-conv algorithm used when algo=0: 1 = exact fp32 FFMA (thread per pair), 2 = tensor cores (3xTF32 mma.sync),
-# 3 = first-generation SIMT kernel (any shape), 4 = tcgen05/TMEM output-stationary implicit GEMM (wide layers).
+# 3 = first-generation SIMT kernel (any shape), 4 = tcgen05/TMEM output-stationary implicit GEMM (wide layers),
+# 5 = exact fp32 block-cooperative FFMA kernel (narrow layers: Cin % 8 == 0, Cout in {8,16,32}; conv_fma.cu).
 # INSMOS_CONV_ALGO overrides for A/B measurements.
 DEFAULT_CONV_ALGO = int(_os.environ.get("INSMOS_CONV_ALGO", "2"))     # measured fastest on B200 in round 1
 # wide layers (>= UMMA_MIN_C input AND output channels, K <= UMMA_MAX_K offsets) go to the tcgen05 kernel
+USE_FMA = _os.environ.get("INSMOS_FMA", "1") != "0"                 # narrow layers on the block-cooperative FFMA kernel
 USE_UMMA = _os.environ.get("INSMOS_UMMA", "1") != "0"
 UMMA_MIN_CIN = int(_os.environ.get("INSMOS_UMMA_MIN_CIN", "32"))
 UMMA_MIN_COUT = int(_os.environ.get("INSMOS_UMMA_MIN_COUT", "32"))
 UMMA_MAX_K = int(_os.environ.get("INSMOS_UMMA_MAX_K", "32"))
 _WIMG_UMMA_CACHE = {}
+
+
+def fma_eligible(K, Cin, Cout):
+    return Cin % 8 == 0 and 8 <= Cin <= 256 and Cout in (8, 16, 32)
 
 
 def umma_eligible(K, Cin, Cout):
@@ -486,6 +492,8 @@ def sparse_conv(feat, weight, rb, scale=None, shift=None, bias=None, residual=No
         if (algo == 2 and USE_UMMA and Cin >= UMMA_MIN_CIN and Cout >= UMMA_MIN_COUT and K <= UMMA_MAX_K
                 and umma_eligible(K, Cin, Cout)):
             algo = 4
+        if algo == 2 and USE_FMA and fma_eligible(K, Cin, Cout) and rb.TM * K < 65536:
+            algo = 5
     wf = prepared_weights(weight) if algo == 2 else None
     if _lib.PROFILE is not None:          # algorithmic bytes / flops of this launch (SURVEY 8d formula)
         P = rb.num_pairs
@@ -499,6 +507,9 @@ def sparse_conv(feat, weight, rb, scale=None, shift=None, bias=None, residual=No
         ws = torch.empty(wsb, dtype=torch.uint8, device=feat.device) if wsb > 0 else None
         call("insmos_sparse_conv_fwd_umma", _p(feat), rb.n_in, Cin, _p(prepared_weight_images(weight)), K, Cout, _p(rb.seg),
              _p(rb.entries), rb.TM, _p(out), rb.n_out, C.byref(ep), _p(ws) if ws is not None else None, wsb, _stream())
+    elif algo == 5:
+        call("insmos_sparse_conv_fwd_fma", _p(feat), rb.n_in, Cin, _p(weight), K, Cout, _p(rb.seg), _p(rb.entries), rb.TM,
+             _p(out), rb.n_out, C.byref(ep), _stream())
     elif algo == 3:
         call("insmos_sparse_conv_fwd", _p(feat), rb.n_in, Cin, _p(weight), K, Cout, _p(rb.seg), _p(rb.entries), rb.TM,
              _p(out), rb.n_out, C.byref(ep), 1, _stream())

@@ -55,6 +55,73 @@ def test_sparse_conv_tile_sizes_and_epilogue(cuda, algo, TM):
     assert torch.allclose(out, ref, rtol=RTOL, atol=ATOL), (out - ref).abs().max()
 
 
+# ---- exact-fp32 block-cooperative FFMA kernel for the narrow layers (algo 5, conv_fma.cu)
+@pytest.mark.parametrize("env", [{}, {"INSMOS_FMA_F2": "1"}, {"INSMOS_FMA_PW": "32"}, {"INSMOS_FMA_PW": "16", "INSMOS_FMA_R": "64"},
+                                 {"INSMOS_FMA_PW": "8", "INSMOS_FMA_WARPS": "4", "INSMOS_FMA_R": "512"}])
+@pytest.mark.parametrize("Cin,Cout", [(8, 8), (16, 8), (8, 16), (24, 16), (16, 32), (48, 32), (32, 32), (64, 16)])
+def test_sparse_conv_fma_matches_oracle(cuda, Cin, Cout, env, monkeypatch):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    cs, c, maps, rb = _setup(cuda, [3, 3, 3, 3])
+    g = torch.Generator().manual_seed(Cin * 1000 + Cout)
+    feats = torch.randn((len(c), Cin), generator=g)
+    W = torch.randn((81, Cin, Cout), generator=g) / np.sqrt(Cin * 20.0)
+    ref = me.conv(feats, W, maps, len(c))
+    out = ops.sparse_conv(feats.to(cuda), W.to(cuda), rb, algo=5).cpu()
+    err = (out - ref).abs().max().item()
+    assert torch.allclose(out, ref, rtol=RTOL, atol=ATOL), "max abs err %.3e (ref max %.3f)" % (err, ref.abs().max())
+
+
+@pytest.mark.parametrize("TM", [16, 32, 64, 128])
+@pytest.mark.parametrize("ksize", [[3, 3, 3, 3], [5, 5, 5, 1], [3, 3, 3, 1]])
+def test_sparse_conv_fma_tile_sizes_epilogue_and_kernels(cuda, TM, ksize):
+    cs, c, maps, _ = _setup(cuda, ksize)
+    K = int(np.prod(ksize))
+    if TM * K >= 65536:
+        pytest.skip("uint16 segment offsets")
+    rb = ops.build_rulebook(cs, cs, ops.spec_me_cube(ksize, [1, 1, 1, 1]), TM=TM)
+    g = torch.Generator().manual_seed(TM + K)
+    Cin, Cout = 16, 16
+    feats = torch.randn((len(c), Cin), generator=g)
+    W = torch.randn((K, Cin, Cout), generator=g) / 18.0
+    scale, shift, bias = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g), torch.randn(Cout, generator=g)
+    res = torch.randn((len(c), Cout), generator=g)
+    ref = torch.relu((me.conv(feats, W, maps, len(c)) + bias) * scale + shift + res)
+    out = ops.sparse_conv(feats.to(cuda), W.to(cuda), rb, scale=scale.to(cuda), shift=shift.to(cuda), bias=bias.to(cuda),
+                          residual=res.to(cuda), relu=True, algo=5).cpu()
+    assert torch.allclose(out, ref, rtol=RTOL, atol=ATOL), (out - ref).abs().max()
+
+
+def test_sparse_conv_fma_strided_transposed_tiny_and_refusals(cuda):
+    """strided / transposed maps, a 3-voxel input, and loud refusal of unsupported shapes."""
+    pts = synth.make_sequence(seed=9, n_scans=3, n_elev=32, n_azim=400)
+    cs, _, _ = ops.voxelize4d(torch.from_numpy(pts).to(cuda), [0.1, 0.1, 0.1, 0.1])
+    coarse, parent = ops.unique_coords(cs.coords, q=[2, 2, 2, 1])
+    c1, c2 = cs.coords.cpu().numpy(), coarse.coords.cpu().numpy()
+    maps = me.kernel_map(c1, c2, [2, 2, 2, 1], [1, 1, 1, 1])
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((len(c1), 8), generator=g)
+    W = torch.randn((8, 8, 16), generator=g) / 4.0
+    down = ops.build_rulebook(coarse, cs, ops.spec_me_cube([2, 2, 2, 1], [1, 1, 1, 1]))
+    out = ops.sparse_conv(x.to(cuda), W.to(cuda), down, algo=5).cpu()
+    assert torch.allclose(out, me.conv(x, W, maps, len(c2)), rtol=RTOL, atol=ATOL)
+    up = ops.build_rulebook(cs, coarse, ops.spec_me_up([2, 2, 2, 1], [2, 2, 2, 1], [1, 1, 1, 1]), parent=parent)
+    y = torch.randn((len(c2), 16), generator=g)
+    Wt = torch.randn((8, 16, 8), generator=g) / 4.0
+    out = ops.sparse_conv(y.to(cuda), Wt.to(cuda), up, algo=5).cpu()
+    assert torch.allclose(out, me.conv(y, Wt, me.transpose_map(maps), len(c1)), rtol=RTOL, atol=ATOL)
+    tiny = torch.tensor([[0, 0, 0, 0, 0], [0, 1, 0, 0, 0], [0, 5, 5, 5, 1]], dtype=torch.int32, device=cuda)
+    ts, _ = ops.unique_coords(tiny)
+    rb = ops.build_rulebook(ts, ts, ops.spec_me_cube([3, 3, 3, 3], [1, 1, 1, 1]))
+    xt = torch.randn((3, 8), generator=g)
+    Wk = torch.randn((81, 8, 8), generator=g)
+    out = ops.sparse_conv(xt.to(cuda), Wk.to(cuda), rb, algo=5).cpu()
+    tm = me.kernel_map(tiny.cpu().numpy(), tiny.cpu().numpy(), [3, 3, 3, 3], [1, 1, 1, 1])
+    assert torch.allclose(out, me.conv(xt, Wk, tm, 3), rtol=RTOL, atol=ATOL)
+    with pytest.raises(RuntimeError):
+        ops.sparse_conv(torch.randn((3, 7)).to(cuda), torch.randn((81, 7, 8)).to(cuda), rb, algo=5)
+
+
 # ---- tcgen05 / TMEM path (algo 4): output-stationary implicit GEMM over 128-row super-tiles
 @pytest.mark.parametrize("Cin,Cout", [(16, 16), (19, 16), (32, 32), (35, 32), (64, 64), (67, 64), (64, 128), (128, 64),
                                       (128, 128), (131, 128), (256, 128), (8, 48)])
@@ -83,7 +150,7 @@ def test_sparse_conv_umma_tile_sizes_epilogue_and_81_offsets(cuda, TM, env, monk
     scale, shift = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g)
     bias = torch.randn(Cout, generator=g)
     res = torch.randn((len(c), Cout), generator=g)
-    ref = torch.relu(me.conv(feats, W, maps, len(c)) * scale + shift + bias + res)
+    ref = torch.relu((me.conv(feats, W, maps, len(c)) + bias) * scale + shift + res)      # BN(conv + bias) + residual
     out = ops.sparse_conv(feats.to(cuda), W.to(cuda), rb, scale=scale.to(cuda), shift=shift.to(cuda), bias=bias.to(cuda),
                           residual=res.to(cuda), relu=True, algo=4).cpu()
     assert torch.allclose(out, ref, rtol=UMMA_RTOL, atol=UMMA_ATOL), (out - ref).abs().max()
