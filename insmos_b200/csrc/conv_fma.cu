@@ -249,7 +249,7 @@ static int launch_fma(FmaArgs a, cudaStream_t st) {
 
 template <int PW, int CL>
 static int dispatch_fma(const FmaArgs& a, cudaStream_t st) {
-    static const bool f2 = env_int("INSMOS_FMA_F2", 0) != 0;
+    const bool f2 = env_int("INSMOS_FMA_F2", 0) != 0;                  // packed FFMA2 variant (A/B switch, read per call)
     if (a.Cin % 16 == 0) return f2 ? launch_fma<16, PW, CL, true>(a, st) : launch_fma<16, PW, CL, false>(a, st);
     if (a.Cin % 8 == 0) return f2 ? launch_fma<8, PW, CL, true>(a, st) : launch_fma<8, PW, CL, false>(a, st);
     return INSMOS_ERR_UNSUPPORTED;

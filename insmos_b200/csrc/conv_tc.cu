@@ -46,6 +46,7 @@ struct TcArgs {
     const float* in; const uint4* wf; const uint16_t* seg; const uint32_t* entries; float* out;
     int64_t n_out, n_tiles; int groups, Cin, Cout, K, TM, KS, NT8;
     int wpt;                                                 // warps sharing one (tile, channel group): bucket k goes to warp k % wpt
+    int terms;                                               // TF32 products per fp32 product: 3 (default, fp32-accurate), 2 or 1 (accuracy study only)
     insmos_epilogue_t ep;
 };
 
@@ -353,9 +354,9 @@ k_spconv_tc4(TcArgs p) {
             split_trunc(clo[ks].y, ah[2], al[2]); split_trunc(chi[ks].y, ah[3], al[3]);
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
-                mma_tf32x(d[j], al, bfrag[j][ks].x, bfrag[j][ks].y);
-                mma_tf32x(d[j], ah, bfrag[j][ks].z, bfrag[j][ks].w);
-                mma_tf32x(d[j], ah, bfrag[j][ks].x, bfrag[j][ks].y);
+                if (p.terms >= 2) mma_tf32x(d[j], al, bfrag[j][ks].x, bfrag[j][ks].y);     // x_lo * w_hi
+                if (p.terms >= 3) mma_tf32x(d[j], ah, bfrag[j][ks].z, bfrag[j][ks].w);     // x_hi * w_lo
+                mma_tf32x(d[j], ah, bfrag[j][ks].x, bfrag[j][ks].y);                        // x_hi * w_hi
             }
         }
         // within a bucket every output row occurs once: plain read-modify-write of the warp's private tile
@@ -601,6 +602,8 @@ extern "C" int insmos_sparse_conv_fwd_tc(const float* in, int64_t n_in, int32_t 
     if (a.ep.scale && !a.ep.shift) return INSMOS_ERR_INVALID_ARG;
     if (n_out == 0) return INSMOS_OK;
     a.groups = a.NT8;
+    a.terms = 3;                              // INSMOS_TF32_TERMS=1|2: accuracy study of cheaper splits (tests/accuracy_tf32_terms.py), never the product default
+    if (const char* e = getenv("INSMOS_TF32_TERMS")) { const int v = atoi(e); if (v == 1 || v == 2) a.terms = v; }
     // >= 64 output channels: weight traffic dominates -> block-cooperative kernel with the slice's weights in smem
     // (measured on B200, C2 workload: 128->128 K=27 430 -> 283 us, 256->128 843 -> 494 us; at 32 channels the
     // per-bucket barriers cost more than the saved traffic: 48->32 K=81 240 -> 550 us)

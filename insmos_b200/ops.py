@@ -422,7 +422,10 @@ import os as _os
 # INSMOS_CONV_ALGO overrides for A/B measurements.
 DEFAULT_CONV_ALGO = int(_os.environ.get("INSMOS_CONV_ALGO", "2"))     # measured fastest on B200 in round 1
 # wide layers (>= UMMA_MIN_C input AND output channels, K <= UMMA_MAX_K offsets) go to the tcgen05 kernel
-USE_FMA = _os.environ.get("INSMOS_FMA", "1") != "0"                 # narrow layers on the block-cooperative FFMA kernel
+# narrow layers on the exact-fp32 block-cooperative FFMA kernel (conv_fma.cu).  OFF by default: measured on B200 (C2 maps,
+# profiles/r02_bench_convs_fma_vs_tc4.jsonl) it is 2.5-3.7x slower than the 3xTF32 mma.sync kernel -- broadcast LDS.128
+# operands cap the FMA pipe at 47 % (profiles/r02_ffma_rate.txt) and the per-phase barriers cost the light layers more.
+USE_FMA = _os.environ.get("INSMOS_FMA", "0") != "0"
 USE_UMMA = _os.environ.get("INSMOS_UMMA", "1") != "0"
 UMMA_MIN_CIN = int(_os.environ.get("INSMOS_UMMA_MIN_CIN", "32"))
 UMMA_MIN_COUT = int(_os.environ.get("INSMOS_UMMA_MIN_COUT", "32"))
