@@ -220,6 +220,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--min-timed-s", type=float, default=MIN_TIMED_S)
+    ap.add_argument("--streams", type=int, default=2, help="forwards in flight on separate CUDA streams / host threads (0: the calling thread only)")
     ap.add_argument("--dump-launches", default=None, help="write the per-C-ABI-call profile of one step (JSON lines)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -255,11 +256,40 @@ def main():
     net = build_model(device)
     gather_out = torch.empty((world, GATHER_PAD_ROWS + 1, 3), dtype=torch.float32, device=device) if world > 1 else None
 
-    def one(i):
-        logits, boxes = step(net, dev[i % n_clouds])
+    # `streams` forwards are kept in flight on separate CUDA streams / host threads (insmos_b200.engine.ForwardPool): the
+    # data-dependent host reads of one sample overlap the kernels of the others.  The exchange step is issued from this
+    # thread in step order (identical collective order on every rank).
+    from insmos_b200.engine import ForwardPool
+    pool = ForwardPool(net, workers=max(args.streams, 1), n_past=N_SCANS) if args.streams > 0 else None
+    main_stream = torch.cuda.current_stream(device)
+
+    def finish(job):
+        logits, boxes = job.wait(main_stream)
+        logits.record_stream(main_stream)
         if world > 1:                                   # the one exchange step: fixed-size all_gather, no host sync
             gather_logits_padded(logits, world, GATHER_PAD_ROWS, out=gather_out)
         return logits
+
+    def one(i):
+        logits, boxes = step(net, dev[i % n_clouds])
+        if world > 1:
+            gather_logits_padded(logits, world, GATHER_PAD_ROWS, out=gather_out)
+        return logits
+
+    def run_steps(k0, k):
+        """k forwards (+ gathers); returns the last logits"""
+        if pool is None:
+            for i in range(k):
+                out = one(k0 + i)
+            return out
+        jobs, out = [], None
+        for i in range(k):
+            jobs.append(pool.submit_points(dev[(k0 + i) % n_clouds]))
+            if len(jobs) > args.streams:
+                out = finish(jobs.pop(0))
+        while jobs:
+            out = finish(jobs.pop(0))
+        return out
 
     # e2e: the public host-buffer path (insmos_b200.pipeline.ScanPipeline, SURVEY 8f N1/N2): raw scans [N_i,4] in host
     # memory + poses -> pinned H2D -> staging kernel (pose transform, time stamps) -> forward -> label kernel -> D2H of
@@ -274,7 +304,8 @@ def main():
         host_scans.append((torch.from_numpy(np.ascontiguousarray(np.concatenate(parts, 0))).pin_memory(), offs))
     poses = [np.eye(4)] * N_SCANS                      # synthetic clouds are already in the newest frame: T = I (same kernel work)
     max_pts = max(int(h.shape[0]) for h in host) + 1024
-    pipe = ScanPipeline(net, dt_pred=0.1, n_scans=N_SCANS, max_points=max_pts, gather_world=world, gather_pad_rows=GATHER_PAD_ROWS)
+    pipe = ScanPipeline(net, dt_pred=0.1, n_scans=N_SCANS, max_points=max_pts, gather_world=world, gather_pad_rows=GATHER_PAD_ROWS,
+                        workers=2 if args.streams > 0 else 0)
 
     def region(e2e):
         """exactly args.steps steps between two events, barrier + synchronize on both sides; -> (ms max over ranks, out)"""
@@ -293,8 +324,7 @@ def main():
             last = pipe.result(prev)
             out = torch.from_numpy(last["labels"])
         else:
-            for i in range(args.steps):
-                out = one(i)
+            out = run_steps(0, args.steps)
         e.record()
         torch.cuda.synchronize()
         ms = torch.tensor([s.elapsed_time(e)], device=device)
@@ -313,7 +343,7 @@ def main():
                     if e2e:
                         pipe.result(pipe.submit_packed(*host_scans[i % n_clouds], poses))
                     else:
-                        one(i)
+                        run_steps(i, 1)
                 launches0 = _lib.launch_count()
                 ms0, out = region(e2e)
                 launches = _lib.launch_count() - launches0
@@ -398,6 +428,7 @@ def main():
                        "l2": "no explicit flush: each step streams > 126 MB (rule books + features) and inputs rotate over %d distinct clouds" % n_clouds,
                        "arithmetic": "fp32; sparse-conv products on tensor cores as 3xTF32 (fp32-accurate) or fp32 FFMA; cuDNN TF32 off",
                        "weights": "tests/golden/insmos_c2.npz (the C2 parity golden's weights)",
+                       "streams": args.streams,
                        "points_per_step": int(dev[0].shape[0]), "current_points": n_cur},
             "timing": {"regions": len(regions), "steps_per_region": args.steps, "timed_s": round(sum(regions) / 1000.0, 3),
                        "ms_per_step_median": round(ms / args.steps, 4), "ms_per_step_min": round(min(regions) / args.steps, 4),

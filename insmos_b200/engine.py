@@ -1,0 +1,94 @@
+"""Concurrent forwards: N host threads, each with its own CUDA stream, run InsMOSNet.forward on independent samples.
+
+Why.  One forward is ~180 kernel launches with ~11 small device->host reads of data-dependent sizes (voxel counts per
+level, candidate count); each read drains the stream and the GPU idles until the host has queued the next kernels
+(measured: 7.0 ms per step for 6.2 ms of kernels), and many of the kernels on the coarse levels do not
+fill 148 SMs.  Samples are independent (models/models.py:313 processes them one by one), so two or three forwards in
+flight on separate streams fill each other's bubbles: the C ABI releases the GIL inside every call (ctypes.CDLL) and the
+reads block outside the GIL.  Streams and threads instead of a static-shape graph capture: every sample has its own shapes.
+"""
+import queue
+import threading
+
+import torch
+
+
+class _Job:
+    __slots__ = ("fn", "args", "ready", "device", "done_event", "result", "error", "finished")
+
+    def __init__(self, fn, args, ready, device):
+        self.fn, self.args, self.ready, self.device = fn, args, ready, device
+        self.done_event, self.result, self.error = None, None, None
+        self.finished = threading.Event()
+
+    def wait(self, stream=None):
+        """block the HOST until the job's kernels are queued, then make `stream` (default: current) wait for them on the
+        DEVICE; returns the job's result.  No device synchronisation on the host."""
+        self.finished.wait()
+        if self.error is not None:
+            raise self.error
+        (stream or torch.cuda.current_stream(self.device)).wait_event(self.done_event)
+        return self.result
+
+
+class StreamWorkers:
+    """`workers` threads bound to `device`, one CUDA stream each; submit(fn, *args) runs fn on the next worker's stream."""
+
+    def __init__(self, device, workers=2):
+        self.device = torch.device(device)
+        self.n = int(workers)
+        self.queues = [queue.Queue() for _ in range(self.n)]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.n)]
+        self.threads = [threading.Thread(target=self._loop, args=(i,), daemon=True) for i in range(self.n)]
+        self._next = 0
+        for t in self.threads:
+            t.start()
+
+    def _loop(self, i):
+        torch.cuda.set_device(self.device)
+        stream = self.streams[i]
+        while True:
+            job = self.queues[i].get()
+            if job is None:
+                return
+            try:
+                with torch.cuda.stream(stream), torch.no_grad():
+                    if job.ready is not None:
+                        stream.wait_event(job.ready)                 # inputs produced on the submitter's stream
+                    job.result = job.fn(*job.args)
+                    job.done_event = torch.cuda.Event()
+                    job.done_event.record(stream)
+            except BaseException as e:                               # surfaced by wait()
+                job.error = e
+            job.finished.set()
+
+    def submit(self, fn, *args, worker=None):
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        job = _Job(fn, args, ready, self.device)
+        w = self._next if worker is None else int(worker) % self.n
+        if worker is None:
+            self._next = (self._next + 1) % self.n
+        self.queues[w].put(job)
+        return job
+
+    def close(self):
+        for q in self.queues:
+            q.put(None)
+        for t in self.threads:
+            t.join(timeout=5)
+
+
+class ForwardPool(StreamWorkers):
+    """forward(points) of one model on `workers` concurrent streams: submit(points) -> job; job.wait() -> (logits, boxes)."""
+
+    def __init__(self, net, workers=2, n_past=10):
+        super().__init__(next(net.parameters()).device, workers)
+        self.net, self.n_past = net, n_past
+
+    def _forward(self, pts):
+        boxes, _, logits = self.net.forward([{"meta": None, "past_point_clouds": pts, "batch_size_npast": self.n_past}], "test")
+        return logits[0], boxes[0][0]
+
+    def submit_points(self, pts):
+        return self.submit(self._forward, pts)

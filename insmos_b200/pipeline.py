@@ -3,9 +3,10 @@
 Mirrors what scripts/predict_mos.py does per sample on the host -- DemoDataset.__getitem__ (:114-159: pose transform in
 float64, timestamps, concatenation), `.cuda()` (:418), and the label step (:436-456: mask, softmax, argmax, label map,
 `.cpu().numpy()`) -- as: ONE pinned host->device copy of the raw scans on a copy stream, one staging kernel, the forward,
-one labelling kernel and two small asynchronous device->host copies into pinned buffers.  Two slots are in flight, so
-the copies of scan k+1 / k-1 overlap the forward of scan k; nothing here is a CPU fallback: the model and the staging
-kernels are CUDA only.
+one labelling kernel and two small asynchronous device->host copies into pinned buffers.  Two slots are in flight, each
+driven by its own host thread and CUDA stream (insmos_b200.engine): the copies and the kernels of scan k+1 fill the
+bubbles that the data-dependent host reads of scan k leave on the GPU; nothing here is a CPU fallback: the model and the
+staging kernels are CUDA only.
 """
 import numpy as np
 import torch
@@ -42,7 +43,8 @@ class ScanPipeline:
     """submit(scans, poses) -> ticket; result(ticket) -> dict(labels int32 [Nc], confidence [Nc,C-1], boxes dict)."""
 
     def __init__(self, model, dt_pred=0.1, n_scans=10, max_points=2_000_000, n_class=3, learning_ignore=None,
-                 learning_map_inv=None, transform=True, device=None, gather_world=1, gather_pad_rows=None, gather_group=None):
+                 learning_map_inv=None, transform=True, device=None, gather_world=1, gather_pad_rows=None, gather_group=None,
+                 workers=2):
         self.model, self.dt, self.n_scans, self.transform = model, float(dt_pred), int(n_scans), bool(transform)
         self.device = device if device is not None else next(model.parameters()).device
         if self.device.type != "cuda":
@@ -52,7 +54,14 @@ class ScanPipeline:
         self.n_class = n_class
         self.ignore_mask = sum(1 << int(k) for k, v in ign.items() if v)
         self.label_map = torch.tensor([int(inv[k]) for k in range(n_class)], dtype=torch.int32, device=self.device)
-        self.copy_stream = torch.cuda.Stream(device=self.device)
+        # workers > 0: each of the two slots is driven by its own host thread and CUDA stream (insmos_b200.engine), so the
+        # data-dependent host reads inside one forward do not stall the other sample; workers = 0: everything is queued
+        # from the calling thread on its current stream (round-1 behaviour)
+        self.workers = None
+        if workers:
+            from insmos_b200.engine import StreamWorkers
+            self.workers = StreamWorkers(self.device, 2)
+        self.copy_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
         # multi-GPU: every rank labels and returns ITS OWN sample; the one exchange step -- the gather of the
         # per-point logits of all ranks -- is a single fixed-size NCCL all_gather queued behind the forward with no host
         # synchronisation (insmos_b200.distributed.gather_logits_padded); the gathered block stays on the device
@@ -115,13 +124,26 @@ class ScanPipeline:
         # t_i = round((i - n + 1) * dt, 3) as float32 (predict_mos.py:147-148,177)
         aux[n * 16:] = np.array([np.float32(round((i - n + 1) * self.dt, 3)) for i in range(n)], dtype=np.float64)
         slot.off_host.numpy()[:] = offs
+        slot.raw_src = raw_pinned
+        ticket = self.next_ticket
+        self.next_ticket += 1
+        slot.meta = {"ticket": ticket, "total": total, "collected": False, "job": None}
+        if self.workers is not None:
+            slot.meta["job"] = self.workers.submit(self._run_slot, slot, ticket % 2, total, use_T, n, worker=ticket % 2)
+        else:
+            self._run_slot(slot, ticket % 2, total, use_T, n)
+        return ticket
+
+    def _run_slot(self, slot, which, total, use_T, n):
+        """queue one sample on the CURRENT stream: H2D (copy stream) -> staging -> forward -> labels -> D2H -> gather."""
         cur = torch.cuda.current_stream(self.device)
-        with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(slot.done)                   # the slot's previous forward has consumed raw_dev
-            slot.raw_dev[:total].copy_(raw_pinned[:total], non_blocking=True)
+        cs = self.copy_streams[which]
+        with torch.cuda.stream(cs):
+            cs.wait_event(slot.done)                                 # the slot's previous forward has consumed raw_dev
+            slot.raw_dev[:total].copy_(slot.raw_src[:total], non_blocking=True)
             slot.aux_dev.copy_(slot.aux_host, non_blocking=True)
             slot.off_dev.copy_(slot.off_host, non_blocking=True)
-            slot.copied.record(self.copy_stream)
+            slot.copied.record(cs)
         cur.wait_event(slot.copied)
         T = slot.aux_dev[:n * 16].view(n, 4, 4) if use_T else None
         stamps = slot.aux_dev[n * 16:].to(torch.float32)
@@ -132,21 +154,28 @@ class ScanPipeline:
         nc = labels.shape[0]
         slot.labels_host[:nc].copy_(labels, non_blocking=True)
         slot.conf_host[:nc].copy_(conf, non_blocking=True)
-        gathered = None
-        if self.gather_world > 1:
-            from insmos_b200.distributed import gather_logits_padded
-            gathered = gather_logits_padded(logits[0], self.gather_world, self.gather_pad_rows, group=self.gather_group,
-                                            out=slot.gather_buf)
         slot.done.record(cur)
-        slot.meta = {"ticket": self.next_ticket, "nc": nc, "boxes": boxes[0][0], "total": total, "collected": False,
-                     "gathered": gathered}
-        self.next_ticket += 1
-        return slot.meta["ticket"]
+        slot.meta.update({"nc": nc, "boxes": boxes[0][0], "logits": logits[0], "gathered": None})
 
     def result(self, ticket):
         slot = self.slots[ticket % 2]
         if slot.meta is None or slot.meta["ticket"] != ticket:
             raise KeyError("ScanPipeline: ticket %d is not in flight" % ticket)
+        if slot.meta["job"] is not None:
+            slot.meta["job"].finished.wait()                         # the worker has queued everything (or failed)
+            if slot.meta["job"].error is not None:
+                raise slot.meta["job"].error
+        if self.gather_world > 1 and slot.meta["gathered"] is None:
+            # the one exchange step, issued HERE -- on the caller's thread and stream, in ticket order -- so that every rank
+            # queues its collectives in the same order whatever the interleaving of the worker threads
+            from insmos_b200.distributed import gather_logits_padded
+            with torch.cuda.device(self.device):
+                main = torch.cuda.current_stream(self.device)
+                main.wait_event(slot.done)
+                lg = slot.meta["logits"]
+                lg.record_stream(main)
+                slot.meta["gathered"] = gather_logits_padded(lg, self.gather_world, self.gather_pad_rows,
+                                                             group=self.gather_group, out=slot.gather_buf)
         slot.done.synchronize()
         nc = slot.meta["nc"]
         slot.meta["collected"] = True
