@@ -321,6 +321,14 @@ int insmos_center_decode(const float* cls, int64_t cls_cs, int64_t cls_ps, const
  * mask = [n*ceil(n/64)] uint64 scratch. keep [<=max_keep] i32 ascending, num_keep [1] i32. */
 int insmos_nms_rotated(const float* boxes, int32_t n, float thresh, int32_t max_keep,
                        unsigned long long* mask, int32_t* keep, int32_t* num_keep, void* stream);
+/* Same result through a PAIR LIST (the default of the host side): the centre-distance test of the dense kernel only appends
+ * the surviving (i, j) pairs to `pairs` (uint2 [pair_cap], insmos_nms_pair_capacity(n) entries suffice for BEV detections),
+ * a second kernel evaluates one pair per thread and ORs the mask bit; if the list overflows the dense kernel runs instead
+ * (decided on the device).  count = uint32 [1] scratch.  Replaces iou3d_nms_cuda.nms_gpu (iou3d_nms.cpp:90-136). */
+int64_t insmos_nms_pair_capacity(int32_t n);
+int insmos_nms_rotated_pairs(const float* boxes, int32_t n, float thresh, int32_t max_keep,
+                             unsigned long long* mask, void* pairs, int64_t pair_cap, uint32_t* count,
+                             int32_t* keep, int32_t* num_keep, void* stream);
 
 /* boxes7 [nb,7] metric (x,y,z,dx,dy,dz,yaw) + labels [nb] -> boxes8 [nb,8] in voxel units of the
  * stride-`stride` level (spconv_unet.py:321-330), fp32 op order preserved. */
@@ -351,6 +359,24 @@ int insmos_stage_scans(const float* raw_xyzi, const int64_t* scan_offsets, int32
  * label_map[argmax] (int32 [n_class], [dev]; NULL = identity).  confidence may be NULL. */
 int insmos_mos_labels(const float* logits, int64_t n, int32_t n_class, uint32_t ignore_mask,
                       const int32_t* label_map, int32_t* labels, float* confidence, void* stream);
+
+/* ---- instance refinement after the forward path (scripts/refine.py:169-302) --------------------------
+ * insmos_point_instance_ids replaces Array_Index.find_point_in_instance_bbox_with_yaw (models/utils/src/Array_Index.cpp:83-149):
+ * points [n,stride] f32 (x,y,z first), boxes8 [nb,8] (cx,cy,cz,dx,dy,dz,yaw,label), out_ground added to the box centre z;
+ * ids [n,ncls] i32 receives box index + 1 in column label-1 (0 = no box; zeroed by the call), with the reference's first-hit
+ * pruning window; where two boxes of one class contain a point the later box wins (the reference's serial order).
+ * first_hit = i32 [nb] scratch. */
+int insmos_point_instance_ids(const float* points, int64_t n, int32_t stride, const float* boxes8, int32_t nb,
+                              float out_ground, int32_t* ids, int32_t ncls, int32_t* first_hit, void* stream);
+/* per-instance reductions of refine.py:208-221: stats [nb,3] i32 = points of instance b+1 (column col of ids), of them
+ * labelled moving_label, of them with conf[j*conf_stride] >= conf_thresh (conf may be NULL). */
+int insmos_instance_stats(const int32_t* ids, int32_t ncls, int32_t col, int64_t n, const int32_t* labels,
+                          int32_t moving_label, const float* conf, int32_t conf_stride, float conf_thresh,
+                          int32_t nb, int32_t* stats, void* stream);
+/* label overwrites of refine.py:240-257,287-292: labels[j] = new_label[id] where id = ids[j,col] > 0 and new_label[id] >= 0;
+ * new_label is i32 [nb+1] (entry 0 unused). */
+int insmos_relabel_instances(const int32_t* ids, int32_t ncls, int32_t col, int64_t n, const int32_t* new_label,
+                             int32_t nb, int32_t* labels, void* stream);
 
 #ifdef __cplusplus
 }

@@ -87,6 +87,11 @@ PROTOTYPES = {
     "insmos_stage_scans": (C.c_int, [_P, _P, _I32, _P, _P, _I32, _P, _I64, _P]),
     "insmos_mos_labels": (C.c_int, [_P, _I64, _I32, C.c_uint32, _P, _P, _P, _P]),
     "insmos_nms_rotated": (C.c_int, [_P, _I32, _F, _I32, _P, _P, _P, _P]),
+    "insmos_point_instance_ids": (C.c_int, [_P, _I64, _I32, _P, _I32, _F, _P, _I32, _P, _P]),
+    "insmos_instance_stats": (C.c_int, [_P, _I32, _I32, _I64, _P, _I32, _P, _I32, _F, _I32, _P, _P]),
+    "insmos_relabel_instances": (C.c_int, [_P, _I32, _I32, _I64, _P, _I32, _P, _P]),
+    "insmos_nms_pair_capacity": (_I64, [_I32]),
+    "insmos_nms_rotated_pairs": (C.c_int, [_P, _I32, _F, _I32, _P, _P, _I64, _P, _P, _P, _P]),
     "insmos_boxes_to_voxel_units": (C.c_int, [_P, _P, _I32, C.POINTER(_F), C.POINTER(_F), _F, _P, _P]),
     "insmos_box_membership": (C.c_int, [_P, _I64, _P, _I32, _F, _P, _I32, _P, _P]),
 }
@@ -133,7 +138,7 @@ KERNELS_PER_CALL = {
     "insmos_linear_fwd": 1,
     "insmos_affine_act": 1, "insmos_concat2": 1, "insmos_pairsum_add": 1, "insmos_gather_rows": 1,
     "insmos_segment_mean": 2, "insmos_build_current_points": 1, "insmos_dense_scatter": 1, "insmos_center_decode": 1,
-    "insmos_nms_rotated": 2, "insmos_boxes_to_voxel_units": 1, "insmos_box_membership": 3,
+    "insmos_nms_rotated": 2, "insmos_point_instance_ids": 3, "insmos_nms_rotated_pairs": 4, "insmos_boxes_to_voxel_units": 1, "insmos_box_membership": 3,
     "insmos_xblock_build": 2, "insmos_rulebook_build_xb": 1, "insmos_rulebook_build_up": 1,
     "insmos_sparse_conv_fwd_umma": 1, "insmos_conv2d_nhwc_umma": 1, "insmos_conv2d_nhwc_tcgen05": 1, "insmos_conv2d_nhwc_tc": 1,
     "insmos_conv_prep_weights_umma": 1, "insmos_bev_prep_weights_tcgen05": 1, "insmos_dense_scatter_nhwc": 1,

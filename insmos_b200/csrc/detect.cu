@@ -172,77 +172,155 @@ k_nms_mask(const float* __restrict__ boxes, int n, float thresh, unsigned long l
     mask[(int64_t)i * col_blocks + cb] = bits;
 }
 
-// greedy sweep on device: 64 boxes at a time.  Thread 0 resolves a block from the diagonal words
-// held in shared memory, then all threads OR the kept rows into the removal words of later blocks
-// (independent, coalesced loads).  Stops as soon as max_keep boxes are kept (only
-// keep[:NMS_POST_MAXSIZE] is ever used: post_process.py:17).
+// ---- pair-list variant of the mask build --------------------------------------------------------
+// ncu of k_nms_mask (profiles/r01_fwd_v7_summary.txt): 0.30 ms at 18 % warps active.  A thread owns a row and walks 64
+// columns; ~0.5 % of the (i, j) pairs pass the centre-distance test, so the ~4 k-instruction rotated-overlap code runs
+// for ONE lane of a warp at a time (40 k executions per 4096 boxes).  Here the distance test only APPENDS the surviving
+// pair to a list, and a second kernel evaluates one pair per thread (32 per warp) and sets the mask bit with atomicOr:
+// the same bits, ~30x fewer executions of the expensive path.  If the list overflows (degenerate input: everything
+// overlaps everything) the dense kernel runs instead -- decided on the device, no host read.
 __global__ void __launch_bounds__(64)
-k_nms_sweep(const unsigned long long* __restrict__ mask, int n, int max_keep, int32_t* __restrict__ keep, int32_t* num_keep) {
-    const int col_blocks = (n + 63) / 64;
-    __shared__ unsigned long long diag2[2][64];                   // diagonal words of block blk (and blk+1, prefetched)
-    __shared__ unsigned long long s_kept;
-    __shared__ int s_num;
-    const int tid = threadIdx.x;
-    // col_blocks <= 64 for n <= 4096; larger n handled by striding words over threads
-    if (tid == 0) s_num = 0;
+k_nms_pairs(const float* __restrict__ boxes, int n, uint2* __restrict__ pairs, unsigned int cap, unsigned int* __restrict__ count) {
+    const int rb = blockIdx.y, cb = blockIdx.x;
+    if (cb < rb) return;                                          // lower triangle is never read by the sweep
+    __shared__ float sb[64 * 7];
+    const int ncol = min(64, n - cb * 64), nrow = min(64, n - rb * 64);
+    if (threadIdx.x < ncol) {
+        const float* s = boxes + (int64_t)(cb * 64 + threadIdx.x) * 7;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) sb[threadIdx.x * 7 + k] = s[k];
+    }
     __syncthreads();
-    // per-thread removal words for columns tid + 64*w are kept in a small local array
-    unsigned long long remv_w[4] = {0ull, 0ull, 0ull, 0ull};     // supports n <= 16384
+    if (threadIdx.x >= nrow) return;
+    const int i = rb * 64 + threadIdx.x;
+    const float ax = boxes[(int64_t)i * 7], ay = boxes[(int64_t)i * 7 + 1], aw = boxes[(int64_t)i * 7 + 3], al = boxes[(int64_t)i * 7 + 4];
+    const float ra = 0.5f * sqrtf(aw * aw + al * al);
+    const int start = (rb == cb) ? threadIdx.x + 1 : 0;
+    for (int j = start; j < ncol; ++j) {
+        const float* b = sb + j * 7;
+        const float dx = ax - b[0], dy = ay - b[1];
+        const float reach = (ra + 0.5f * sqrtf(b[3] * b[3] + b[4] * b[4])) * 1.001f + 0.05f;     // same exact early-out as k_nms_mask
+        if (dx * dx + dy * dy > reach * reach) continue;
+        const unsigned int pos = atomicAdd(count, 1u);
+        if (pos < cap) pairs[pos] = make_uint2((unsigned)i, (unsigned)(cb * 64 + j));
+    }
+}
+__global__ void __launch_bounds__(128)
+k_nms_pair_iou(const float* __restrict__ boxes, int n, float thresh, const uint2* __restrict__ pairs, unsigned int cap,
+               const unsigned int* __restrict__ count, unsigned long long* __restrict__ mask) {
+    const unsigned int total = *count;
+    if (total > cap) return;                                      // overflow: the dense kernel takes over
+    const int col_blocks = (n + 63) / 64;
+    for (unsigned int p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += gridDim.x * blockDim.x) {
+        const uint2 ij = pairs[p];
+        float a[7], b[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) { a[k] = boxes[(int64_t)ij.x * 7 + k]; b[k] = boxes[(int64_t)ij.y * 7 + k]; }
+        if (rot_iou_bev(a, b) > thresh)
+            atomicOr(mask + (int64_t)ij.x * col_blocks + (ij.y >> 6), 1ull << (ij.y & 63u));
+    }
+}
+// dense fallback, skipped unless the pair list overflowed
+__global__ void __launch_bounds__(64)
+k_nms_mask_if_overflow(const float* __restrict__ boxes, int n, float thresh, unsigned long long* __restrict__ mask,
+                       const unsigned int* __restrict__ count, unsigned int cap);
+
+// greedy sweep on device: 64 boxes at a time.  Thread 0 resolves a block from the diagonal words held in shared memory
+// (branch-free body: the 64 diagonal loads do not depend on the decisions), then 256 threads OR the kept rows into the
+// removal words of the later blocks: thread = (column word, quarter of the kept rows), all loads of a quarter issued before
+// any is consumed.  Stops as soon as max_keep boxes are kept (only keep[:NMS_POST_MAXSIZE] is ever used: post_process.py:17).
+#define SW_THREADS 256
+__global__ void __launch_bounds__(SW_THREADS)
+k_nms_sweep(const unsigned long long* __restrict__ mask, int n, int max_keep, int32_t* __restrict__ keep, int32_t* num_keep) {
+    const int col_blocks = (n + 63) / 64;                          // <= 256 (n <= 16384)
+    __shared__ unsigned long long diag2[2][64];                   // diagonal words of block blk (and blk+1, prefetched)
+    __shared__ unsigned long long remv[256];                      // removal word of every column block
+    __shared__ unsigned long long part[SW_THREADS];
+    __shared__ int s_list[64];
+    __shared__ int s_nk, s_num;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_num = 0;
+    remv[tid] = 0ull;
     if (tid < min(64, n)) diag2[0][tid] = mask[(int64_t)tid * col_blocks];
+    __syncthreads();
     for (int blk = 0; blk < col_blocks; ++blk) {
         const int base = blk * 64;
         const int cnt = min(64, n - base);
-        unsigned long long* diag = diag2[blk & 1];
+        const unsigned long long* diag = diag2[blk & 1];
         // the next block's diagonal does not depend on this block's outcome: fetch it now, one L2 round trip off the chain
         unsigned long long nd = 0ull;
-        const bool pf = (blk + 1 < col_blocks) && (base + 64 + tid < n);
+        const bool pf = tid < 64 && (blk + 1 < col_blocks) && (base + 64 + tid < n);
         if (pf) nd = mask[(int64_t)(base + 64 + tid) * col_blocks + blk + 1];
-        // removal word of this block lives in thread (blk & 63), slot (blk >> 6)
-        __shared__ unsigned long long s_r;
-        if (tid == (blk & 63)) s_r = remv_w[blk >> 6];
-        __syncthreads();
         if (tid == 0) {
-            unsigned long long r = s_r, kept = 0ull;
-            int num = s_num;
-            for (int i = 0; i < cnt && num < max_keep; ++i) {
-                if (!((r >> i) & 1ull)) {
-                    kept |= 1ull << i;
-                    keep[num++] = base + i;
-                    r |= diag[i];
-                }
+            unsigned long long r = remv[blk];
+            int num = s_num, nk = 0;
+            for (int i = 0; i < cnt; ++i) {
+                const unsigned long long d = diag[i];
+                const bool k = !((r >> i) & 1ull) && num < max_keep;
+                if (k) { keep[num] = base + i; s_list[nk] = i; }
+                num += k; nk += k;
+                r |= k ? d : 0ull;
             }
-            s_kept = kept; s_num = num;
+            s_nk = nk; s_num = num;
         }
         __syncthreads();
         if (s_num >= max_keep) break;
         if (pf) diag2[(blk + 1) & 1][tid] = nd;
-        unsigned long long kept = s_kept;
-        while (kept) {
-            // up to 8 kept rows per step: all loads are issued before any is consumed (one L2 round trip per batch
-            // instead of one per kept box)
-            int idx[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                idx[u] = kept ? (__ffsll((long long)kept) - 1) : -1;
-                kept &= kept - 1;
-            }
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const int c = tid + 64 * w;
-                if (c > blk && c < col_blocks) {
+        const int nk = s_nk;
+        // OR the kept rows into the removal words of the later column blocks
+        for (int c0 = blk + 1; c0 < col_blocks; c0 += 64) {
+            const int c = c0 + (tid & 63), qtr = tid >> 6;
+            unsigned long long o = 0ull;
+            if (c < col_blocks) {
+                for (int u0 = qtr; u0 < nk; u0 += 32) {            // this quarter's rows: u0, u0+4, ... ; 8 loads in flight
                     unsigned long long v[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = (idx[u] >= 0) ? mask[(int64_t)(base + idx[u]) * col_blocks + c] : 0ull;
-                    unsigned long long o = 0ull;
+                    for (int u = 0; u < 8; ++u) {
+                        const int k = u0 + 4 * u;
+                        v[u] = (k < nk) ? mask[(int64_t)(base + s_list[k]) * col_blocks + c] : 0ull;
+                    }
 #pragma unroll
                     for (int u = 0; u < 8; ++u) o |= v[u];
-                    remv_w[w] |= o;
                 }
             }
+            part[tid] = o;
+            __syncthreads();
+            if (tid < 64 && c < col_blocks) remv[c] |= part[tid] | part[tid + 64] | part[tid + 128] | part[tid + 192];
+            __syncthreads();
         }
-        __syncthreads();
     }
     if (tid == 0) *num_keep = s_num;
+}
+
+__global__ void __launch_bounds__(64)
+k_nms_mask_if_overflow(const float* __restrict__ boxes, int n, float thresh, unsigned long long* __restrict__ mask,
+                       const unsigned int* __restrict__ count, unsigned int cap) {
+    if (*count <= cap) return;
+    const int rb = blockIdx.y, cb = blockIdx.x;
+    const int col_blocks = (n + 63) / 64;
+    __shared__ float sb[64 * 7];
+    const int ncol = min(64, n - cb * 64), nrow = min(64, n - rb * 64);
+    if (threadIdx.x < ncol) {
+        const float* s = boxes + (int64_t)(cb * 64 + threadIdx.x) * 7;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) sb[threadIdx.x * 7 + k] = s[k];
+    }
+    __syncthreads();
+    if (threadIdx.x >= nrow || cb < rb) return;
+    const int i = rb * 64 + threadIdx.x;
+    float a[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) a[k] = boxes[(int64_t)i * 7 + k];
+    unsigned long long bits = 0ull;
+    const int start = (rb == cb) ? threadIdx.x + 1 : 0;
+    for (int j = start; j < ncol; ++j)
+        if (rot_iou_bev(a, sb + j * 7) > thresh) bits |= 1ull << j;
+    mask[(int64_t)i * col_blocks + cb] = bits;
+}
+
+extern "C" int64_t insmos_nms_pair_capacity(int32_t n) {
+    // ~20 spatial neighbours per box in a dense BEV map; 128 per box is generous and keeps the list at 4 MB for 4096 boxes
+    return n <= 0 ? 0 : (int64_t)n * 128;
 }
 
 extern "C" int insmos_nms_rotated(const float* boxes, int32_t n, float thresh, int32_t max_keep,
@@ -254,7 +332,32 @@ extern "C" int insmos_nms_rotated(const float* boxes, int32_t n, float thresh, i
     const int cb = (n + 63) / 64;
     k_nms_mask<<<dim3(cb, cb), 64, 0, st>>>(boxes, n, thresh, mask);
     INSMOS_CHECK_LAUNCH("k_nms_mask");
-    k_nms_sweep<<<1, 64, 0, st>>>(mask, n, max_keep, keep, num_keep);
+    k_nms_sweep<<<1, SW_THREADS, 0, st>>>(mask, n, max_keep, keep, num_keep);
+    INSMOS_CHECK_LAUNCH("k_nms_sweep");
+    return INSMOS_OK;
+}
+
+// same result as insmos_nms_rotated through the pair list: pairs = uint2 [pair_cap] scratch, count = uint32 [1] scratch
+extern "C" int insmos_nms_rotated_pairs(const float* boxes, int32_t n, float thresh, int32_t max_keep,
+                                        unsigned long long* mask, void* pairs, int64_t pair_cap, uint32_t* count,
+                                        int32_t* keep, int32_t* num_keep, void* stream) {
+    if ((n > 0 && !boxes) || !mask || !keep || !num_keep || n < 0 || max_keep <= 0) return INSMOS_ERR_INVALID_ARG;
+    if (n > 16384) return INSMOS_ERR_UNSUPPORTED;
+    if (thresh < 0.0f || !pairs || !count || pair_cap <= 0 || pair_cap > 0x7fffffffll)
+        return insmos_nms_rotated(boxes, n, thresh, max_keep, mask, keep, num_keep, stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { INSMOS_CHECK_CUDA(cudaMemsetAsync(num_keep, 0, sizeof(int32_t), st)); return INSMOS_OK; }
+    const int cb = (n + 63) / 64;
+    INSMOS_CHECK_CUDA(cudaMemsetAsync(mask, 0, sizeof(unsigned long long) * (size_t)n * cb, st));
+    INSMOS_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), st));
+    k_nms_pairs<<<dim3(cb, cb), 64, 0, st>>>(boxes, n, reinterpret_cast<uint2*>(pairs), (unsigned)pair_cap, count);
+    INSMOS_CHECK_LAUNCH("k_nms_pairs");
+    const int64_t blocks = ceil_div64(pair_cap, 128) < 148 * 8 ? ceil_div64(pair_cap, 128) : 148 * 8;
+    k_nms_pair_iou<<<(unsigned)blocks, 128, 0, st>>>(boxes, n, thresh, reinterpret_cast<const uint2*>(pairs), (unsigned)pair_cap, count, mask);
+    INSMOS_CHECK_LAUNCH("k_nms_pair_iou");
+    k_nms_mask_if_overflow<<<dim3(cb, cb), 64, 0, st>>>(boxes, n, thresh, mask, count, (unsigned)pair_cap);
+    INSMOS_CHECK_LAUNCH("k_nms_mask_if_overflow");
+    k_nms_sweep<<<1, SW_THREADS, 0, st>>>(mask, n, max_keep, keep, num_keep);
     INSMOS_CHECK_LAUNCH("k_nms_sweep");
     return INSMOS_OK;
 }

@@ -679,8 +679,13 @@ def dense_scatter_nhwc(feat, coords, D, H, W):
     return out
 
 
-def nms_rotated(boxes_sorted, thresh, max_keep):
-    """boxes [n,7] sorted by descending score -> keep indices (ascending, <= max_keep) as i32 tensor."""
+NMS_DENSE = _os.environ.get("INSMOS_NMS_DENSE", "0") != "0"        # A/B switch: the round-1 dense mask kernel
+
+
+def nms_rotated(boxes_sorted, thresh, max_keep, dense=None):
+    """boxes [n,7] sorted by descending score -> keep indices (ascending, <= max_keep) as i32 tensor.
+    dense=True: every (i, j) of the upper triangle through the rotated-overlap code (the reference's kernel shape);
+    default: pair list (distance test -> compact list -> one pair per thread), same keep list."""
     boxes_sorted = _req(boxes_sorted, F32, "nms_rotated")
     n = boxes_sorted.shape[0]
     dev = boxes_sorted.device
@@ -688,7 +693,14 @@ def nms_rotated(boxes_sorted, thresh, max_keep):
     mask = torch.empty(max(n * cb, 1), dtype=torch.int64, device=dev)
     keep = torch.empty(max(min(n, max_keep), 1), dtype=I32, device=dev)
     num = torch.zeros(1, dtype=I32, device=dev)
-    call("insmos_nms_rotated", _p(boxes_sorted), n, float(thresh), int(max_keep), _p(mask), _p(keep), _p(num), _stream())
+    if NMS_DENSE if dense is None else dense:
+        call("insmos_nms_rotated", _p(boxes_sorted), n, float(thresh), int(max_keep), _p(mask), _p(keep), _p(num), _stream())
+    else:
+        cap = int(_lib.load().insmos_nms_pair_capacity(n))
+        pairs = torch.empty((max(cap, 1), 2), dtype=I32, device=dev)
+        count = torch.empty(1, dtype=I32, device=dev)
+        call("insmos_nms_rotated_pairs", _p(boxes_sorted), n, float(thresh), int(max_keep), _p(mask), _p(pairs), cap, _p(count),
+             _p(keep), _p(num), _stream())
     return keep[:int(num.item())]
 
 

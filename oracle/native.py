@@ -25,6 +25,9 @@ def lib():
         L.oracle_nms.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_void_p]
         L.oracle_find_features_by_bbox_with_yaw.restype = None
         L.oracle_find_features_by_bbox_with_yaw.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.oracle_find_point_in_instance_bbox_with_yaw.restype = None
+        L.oracle_find_point_in_instance_bbox_with_yaw.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                                                  C.c_int, C.c_float]
         _lib = L
     return _lib
 
@@ -48,6 +51,15 @@ def find_features_by_bbox_with_yaw(vox_xyz, boxes8, n_class=3):
     v = np.ascontiguousarray(vox_xyz, dtype=np.int32); b = np.ascontiguousarray(boxes8, dtype=np.float32)
     out = np.zeros((len(v), n_class), dtype=np.int32)
     lib().oracle_find_features_by_bbox_with_yaw(v.ctypes.data, len(v), b.ctypes.data, len(b), out.ctypes.data, n_class)
+    return out
+
+
+def find_point_in_instance_bbox_with_yaw(points, boxes8, out_ground, n_class=3):
+    """refine.py:196: per-point instance ids [n,n_class] int32 (box index + 1 in column label-1), serial box order."""
+    pts = np.ascontiguousarray(points, dtype=np.float32); b = np.ascontiguousarray(boxes8, dtype=np.float32)
+    out = np.zeros((len(pts), n_class), dtype=np.int32)
+    lib().oracle_find_point_in_instance_bbox_with_yaw(pts.ctypes.data, len(pts), pts.shape[1], b.ctypes.data, len(b),
+                                                      out.ctypes.data, n_class, C.c_float(out_ground))
     return out
 
 

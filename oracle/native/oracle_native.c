@@ -163,3 +163,36 @@ void oracle_find_features_by_bbox_with_yaw(const int32_t* vox, int n, const floa
         }
     }
 }
+
+/* Array_Index.find_point_in_instance_bbox_with_yaw (models/utils/src/Array_Index.cpp:83-149), boxes visited in ascending
+ * order (the reference's OpenMP loop over boxes races when two boxes of one class contain the same point; serial order =
+ * the later box wins).  pts [n,stride] float (x,y,z first), boxes [nb,8] (cx,cy,cz,dx,dy,dz,yaw,label), out [n,ncls] int32
+ * (caller zeroes it): out[j,label-1] = box index + 1. */
+void oracle_find_point_in_instance_bbox_with_yaw(const float* pts, int n, int stride, const float* boxes, int nb,
+                                                 int32_t* out, int ncls, float out_ground) {
+    for (int i = 0; i < nb; ++i) {
+        const float* b = boxes + (size_t)i * 8;
+        float center[3] = {b[0], b[1], b[2] + out_ground}, extend[3] = {b[3], b[4], b[5]};
+        float theta = b[6];
+        float cos_theta = cosf(theta), sin_theta = sinf(theta);
+        int first_flag = 0;
+        float first_point[3] = {0.f, 0.f, 0.f};
+        for (int j = 0; j < n; ++j) {
+            const float* r = pts + (size_t)j * stride;
+            if (first_flag == 1 &&
+                (r[0] > (first_point[0] + extend[0]) || r[0] < (first_point[0] - extend[0]) ||
+                 r[1] > (first_point[1] + extend[1]) || r[1] < (first_point[1] - extend[1]) ||
+                 r[2] > (first_point[2] + extend[2]) || r[2] < (first_point[2] - extend[2])))
+                continue;
+            float centered[3] = {r[0] - center[0], r[1] - center[1], r[2] - center[2]};
+            float rx = centered[0] * cos_theta + centered[1] * sin_theta;
+            float ry = -centered[0] * sin_theta + centered[1] * cos_theta;
+            if (rx <= extend[0] / 2 && rx >= -extend[0] / 2 && ry <= extend[1] / 2 && ry >= -extend[1] / 2 &&
+                centered[2] <= extend[2] / 2 && centered[2] >= -extend[2] / 2) {
+                int label = (int)b[7];
+                if (label > 0 && label <= ncls) out[(size_t)j * ncls + label - 1] = i + 1;
+                if (!first_flag) { first_flag = 1; first_point[0] = r[0]; first_point[1] = r[1]; first_point[2] = r[2]; }
+            }
+        }
+    }
+}

@@ -43,6 +43,18 @@ def test_nms_matches_oracle(cuda, n, spread):
     assert empty.numel() == 0
 
 
+@pytest.mark.parametrize("n,spread", [(5, 1.0), (64, 3.0), (1000, 6.0), (4096, 40.0), (4096, 4.0), (600, 0.5)])
+def test_nms_pair_list_equals_dense_mask(cuda, n, spread):
+    """the pair-list build (default) and the dense upper-triangle build give the same keep list bit for bit; spread 0.5 /
+    4.0 make almost every pair overlap, which overflows the list and exercises the on-device fallback."""
+    rng = np.random.default_rng(1000 + n)
+    b = torch.from_numpy(_boxes(rng, n, spread)).to(cuda)
+    for max_keep in (500, 100000):
+        a = ops.nms_rotated(b, 0.01, max_keep, dense=True)
+        c = ops.nms_rotated(b, 0.01, max_keep, dense=False)
+        assert torch.equal(a, c), (n, spread, max_keep, a[:10], c[:10])
+
+
 def test_nms_matches_reference_cuda_kernel(cuda):
     ref = native.ref_iou3d()
     if ref is None:
