@@ -143,7 +143,7 @@ def cpu_port_full(sd_cpu, budget_s, max_steps):
             "unet_encoder_s": timing.get("unet_encoder_s"), "bev_s": timing.get("bev_s"), "decoder_s": timing.get("decoder_s")}
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, out_stream):
     if rank != 0:
         return
     sd = golden_state_dict()
@@ -156,10 +156,11 @@ def run_reference(args, rank):
                        "(oracle/graph.py) on the full C2 cloud with the golden's weights; one full-size forward takes ~1 min, so "
                        "the run times as many steps as fit ~3 min and reports that count (steps) with no warm-up"},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    out_stream.write(json.dumps(line) + "\n")
+    out_stream.flush()
 
 
-def run_c4(args, device):
+def run_c4(args, device, out_stream):
     """BASELINE config 4: 300 k points per scan x 10, voxel 0.05 m -- per-map build time / pairs and the gather-scatter
     kernels' algorithmic GB/s (the 100 k-voxel cap makes the full model meaningless at this density)."""
     from insmos_b200 import ops, synth, _lib
@@ -206,12 +207,23 @@ def run_c4(args, device):
             rows.append({"op": "sparse_conv %s %d->%d" % (name, Cin, Cout), "ms": round(ms, 4), "pairs": P,
                          "alg_GBps": round(b / ms / 1e6, 1), "frac_of_peak": round(b / ms / 1e6 / peak, 4),
                          "gflops": round(2 * P * Cin * Cout / ms / 1e6, 1)})
-    print(json.dumps({"metric": "c4_sweep", "workload": "C4: N=10 x 300k pts (3.0 M points), voxel 0.05 m: rule-book build + "
+    out_stream.write(json.dumps({"metric": "c4_sweep", "workload": "C4: N=10 x 300k pts (3.0 M points), voxel 0.05 m: rule-book build + "
                       "gather/scatter sparse conv sweep", "peak_GBps": peak, "peak_source": peak_src, "reps": reps, "rows": rows,
-                      "gpu_launches": _lib.launch_count()}))
+                      "gpu_launches": _lib.launch_count()}) + "\n")
+    out_stream.flush()
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: everything else any library writes to fd 1 (NCCL's version banner, torchrun
+    notices) is sent to stderr; returns the stream that still points at the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
+    out_stream = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -227,7 +239,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, out_stream)
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU port)")
@@ -236,7 +248,7 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     if args.workload == "c4":
-        run_c4(args, device)
+        run_c4(args, device, out_stream)
         return
     # every distinct input cloud is seen once before the timed region (first-touch sizes hit cudaMalloc in the caching
     # allocator: measured 9.4 -> 11.4 ms/step when the 4th cloud first appeared inside the timed loop)
@@ -244,8 +256,6 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"              # stdout carries exactly one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=device)
     from insmos_b200 import _lib
     from insmos_b200.distributed import gather_logits_padded
@@ -448,7 +458,8 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        out_stream.write(json.dumps(line) + "\n")
+        out_stream.flush()
     if dist:
         dist.destroy_process_group()
 

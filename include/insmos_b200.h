@@ -285,17 +285,12 @@ int insmos_build_current_points(const float* points, int32_t point_stride, const
 int insmos_dense_scatter(const float* feat, const int32_t* coords, int64_t n, int32_t C,
                          int32_t D, int32_t H, int32_t W, float* out, void* stream);
 
-/* Dense BEV convolutions on tensor cores (3xTF32, fp32-accurate), NHWC activations [H*W, C] (a9;
- * base_bev_backbone.py:84-115).  weight [taps, Cin, Cout] f32 with BatchNorm(eval) pre-folded, bias [Cout] or NULL.
- * mode 0: 3x3 stride 1 zero-pad 1 (taps=9, tap = ky*3+kx); mode 1: 1x1 (taps=1); mode 2: 2x2 stride-2 transposed
- * conv (taps=4, tap = dy*2+dx, out is [2H*2W, Cout]).  Requires Cin % 32 == 0 and Cout % 128 == 0. */
-int insmos_conv2d_nhwc_tc(const float* in, int32_t H, int32_t W, int32_t Cin,
-                          const float* weight, int32_t mode, int32_t Cout,
-                          const float* bias, int32_t relu, float* out, void* stream);
-
-/* Same convolution on the 5th-generation tensor cores: tcgen05.mma kind::tf32 (3xTF32 split), accumulators in TMEM,
- * weight tiles by TMA bulk copy, mbarrier pipeline (bev_tcgen05.cu).  The weights are first rearranged once per layer
- * into pre-swizzled TF32 hi/lo tile images (wimg: insmos_bev_wimg_elems(...) floats). */
+/* Dense BEV convolutions (a9; base_bev_backbone.py:84-115; the reference runs them through cuDNN) on the 5th-generation
+ * tensor cores: tcgen05.mma kind::tf32 (3xTF32 split, fp32-accurate), accumulators in TMEM, weight tiles by TMA bulk copy,
+ * mbarrier pipeline (bev_tcgen05.cu).  NHWC activations [H*W, C]; weight [taps, Cin, Cout] f32 with BatchNorm(eval)
+ * pre-folded, rearranged once per layer into pre-swizzled TF32 hi/lo tile images (wimg: insmos_bev_wimg_elems(...) floats);
+ * bias [Cout] or NULL.  mode 0: 3x3 stride 1 zero-pad 1 (taps=9, tap = ky*3+kx); mode 1: 1x1 (taps=1); mode 2: 2x2
+ * stride-2 transposed conv (taps=4, tap = dy*2+dx, out is [2H*2W, Cout]).  Requires Cin % 32 == 0 and Cout % 128 == 0. */
 int64_t insmos_bev_wimg_elems(int32_t taps, int32_t Cin, int32_t Cout);
 int insmos_bev_prep_weights_tcgen05(const float* weight, int32_t taps, int32_t Cin, int32_t Cout, float* wimg, void* stream);
 int insmos_conv2d_nhwc_tcgen05(const float* in, int32_t H, int32_t W, int32_t Cin,

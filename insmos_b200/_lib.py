@@ -79,7 +79,6 @@ PROTOTYPES = {
     "insmos_build_current_points": (C.c_int, [_P, _I32, _P, _I64, _P, _P, _I32, _I32, _P, _P]),
     "insmos_dense_scatter": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P]),
     "insmos_center_decode": (C.c_int, [_P, _I64, _I64, _P, _I64, _I64, _I32, _I32, _I32, _F, _F, _F, _F, _F, _P, _P, _P, _P]),
-    "insmos_conv2d_nhwc_tc": (C.c_int, [_P, _I32, _I32, _I32, _P, _I32, _I32, _P, _I32, _P, _P]),
     "insmos_dense_scatter_nhwc": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P]),
     "insmos_bev_wimg_elems": (_I64, [_I32, _I32, _I32]),
     "insmos_bev_prep_weights_tcgen05": (C.c_int, [_P, _I32, _I32, _I32, _P, _P]),
@@ -140,7 +139,7 @@ KERNELS_PER_CALL = {
     "insmos_segment_mean": 2, "insmos_build_current_points": 1, "insmos_dense_scatter": 1, "insmos_center_decode": 1,
     "insmos_nms_rotated": 2, "insmos_point_instance_ids": 3, "insmos_nms_rotated_pairs": 4, "insmos_boxes_to_voxel_units": 1, "insmos_box_membership": 3,
     "insmos_xblock_build": 2, "insmos_rulebook_build_xb": 1, "insmos_rulebook_build_up": 1,
-    "insmos_sparse_conv_fwd_umma": 1, "insmos_conv2d_nhwc_umma": 1, "insmos_conv2d_nhwc_tcgen05": 1, "insmos_conv2d_nhwc_tc": 1,
+    "insmos_sparse_conv_fwd_umma": 1, "insmos_conv2d_nhwc_umma": 1, "insmos_conv2d_nhwc_tcgen05": 1,
     "insmos_conv_prep_weights_umma": 1, "insmos_bev_prep_weights_tcgen05": 1, "insmos_dense_scatter_nhwc": 1,
 }
 PROFILE = None        # list collecting (name, start_event, end_event, meta) when profiling is on

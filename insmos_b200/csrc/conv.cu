@@ -122,155 +122,6 @@ extern "C" int insmos_conv_prep_weights(const float* weight, int32_t K, int32_t 
     return INSMOS_OK;
 }
 
-#if 0   // v2 kernel, superseded by conv_tc.cu (kept out of the build; see profiles/r01_conv_v2_sass_notes.md)
-#define MMA_WARPS 4
-template <int NT>
-__global__ void __launch_bounds__(MMA_WARPS * 32)
-k_spconv_tc(const float* __restrict__ in, const uint4* __restrict__ wf,
-            const uint16_t* __restrict__ seg, const uint32_t* __restrict__ entries,
-            float* __restrict__ out, int64_t n_out, int64_t n_tiles, int groups, int Cin, int Cout, int K, int TM,
-            int KS, int NT8, insmos_epilogue_t ep) {
-    constexpr int CW = NT * 8;                               // channel columns owned by this warp
-    extern __shared__ __align__(16) float sm[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const int64_t wglobal = (int64_t)blockIdx.x * MMA_WARPS + warp;
-    const int64_t tile = wglobal / groups;
-    const int grp = (int)(wglobal - tile * groups);
-    if (tile >= n_tiles) return;                             // warps are independent: no block barrier below
-    float* acc = sm + (size_t)warp * TM * CW;                // [TM][CW]
-    int* sseg = reinterpret_cast<int*>(sm + (size_t)MMA_WARPS * TM * CW) + warp * (K + 1);
-    const uint16_t* tseg = seg + tile * (K + 1);
-    for (int k = lane; k <= K; k += 32) sseg[k] = tseg[k];
-    for (int i = lane; i < TM * CW; i += 32) acc[i] = 0.0f;
-    __syncwarp();
-    const uint32_t* tent = entries + tile * (int64_t)TM * K;
-    const bool even = (Cin & 1) == 0;
-    const int nt0 = grp * NT;
-
-    // chunk iterator over the non-empty buckets: (k, s0, n, c0)
-    int k = -1, s0 = 0, n = 0, c0 = 0;
-    auto advance = [&]() -> bool {
-        c0 += 16;
-        while (c0 >= n) {
-            if (++k >= K) return false;
-            s0 = sseg[k]; n = sseg[k + 1] - s0; c0 = 0;
-        }
-        return true;
-    };
-    bool have = advance();
-    bool v_lo = false, v_hi = false;
-    uint32_t e_lo = 0u, e_hi = 0u;
-    if (have) {
-        v_lo = (c0 + g) < n; v_hi = (c0 + g + 8) < n;
-        if (v_lo) e_lo = __ldg(tent + s0 + c0 + g);
-        if (v_hi) e_hi = __ldg(tent + s0 + c0 + g + 8);
-    }
-    while (have) {
-        const int kc = k;
-        const bool cv_lo = v_lo, cv_hi = v_hi;
-        const uint32_t ce_lo = e_lo, ce_hi = e_hi;
-        have = advance();                                    // prefetch the next chunk's entries
-        if (have) {
-            v_lo = (c0 + g) < n; v_hi = (c0 + g + 8) < n;
-            e_lo = v_lo ? __ldg(tent + s0 + c0 + g) : 0u;
-            e_hi = v_hi ? __ldg(tent + s0 + c0 + g + 8) : 0u;
-        }
-        const float* x_lo = in + (int64_t)(ce_lo & INSMOS_ROW_MASK) * Cin;
-        const float* x_hi = in + (int64_t)(ce_hi & INSMOS_ROW_MASK) * Cin;
-        const uint4* wk = wf + ((int64_t)kc * NT8 + nt0) * KS * 32 + lane;
-        float d[NT][4];
-#pragma unroll
-        for (int j = 0; j < NT; ++j) { d[j][0] = d[j][1] = d[j][2] = d[j][3] = 0.0f; }
-#pragma unroll 2
-        for (int ks = 0; ks < KS; ++ks) {
-            const int col = ks * 8 + 2 * t;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // (g,2t) (g+8,2t) (g,2t+1) (g+8,2t+1)
-            if (even) {
-                if (col < Cin) {
-                    if (cv_lo) { const float2 v = __ldg(reinterpret_cast<const float2*>(x_lo + col)); a0 = v.x; a2 = v.y; }
-                    if (cv_hi) { const float2 v = __ldg(reinterpret_cast<const float2*>(x_hi + col)); a1 = v.x; a3 = v.y; }
-                }
-            } else {
-                if (col < Cin) { if (cv_lo) a0 = __ldg(x_lo + col); if (cv_hi) a1 = __ldg(x_hi + col); }
-                if (col + 1 < Cin) { if (cv_lo) a2 = __ldg(x_lo + col + 1); if (cv_hi) a3 = __ldg(x_hi + col + 1); }
-            }
-            uint4 b[NT];
-#pragma unroll
-            for (int j = 0; j < NT; ++j) b[j] = __ldg(wk + ((int64_t)j * KS + ks) * 32);
-            uint32_t ah[4], al[4];
-            split_tf32(a0, ah[0], al[0]); split_tf32(a1, ah[1], al[1]);
-            split_tf32(a2, ah[2], al[2]); split_tf32(a3, ah[3], al[3]);
-#pragma unroll
-            for (int j = 0; j < NT; ++j) {
-                mma_tf32(d[j], al, b[j].x, b[j].y);
-                mma_tf32(d[j], ah, b[j].z, b[j].w);
-                mma_tf32(d[j], ah, b[j].x, b[j].y);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < NT; ++j) {
-            const int cc = j * 8 + 2 * t;
-            if (cv_lo) {
-                float2* p = reinterpret_cast<float2*>(acc + (ce_lo >> INSMOS_ROW_BITS) * CW + cc);
-                float2 v = *p; v.x += d[j][0]; v.y += d[j][1]; *p = v;
-            }
-            if (cv_hi) {
-                float2* p = reinterpret_cast<float2*>(acc + (ce_hi >> INSMOS_ROW_BITS) * CW + cc);
-                float2 v = *p; v.x += d[j][2]; v.y += d[j][3]; *p = v;
-            }
-        }
-        __syncwarp();
-    }
-    const int64_t row0 = tile * TM;
-    const int rows = (int)((n_out - row0) < TM ? (n_out - row0) : TM);
-    const int cbase = nt0 * 8;
-    for (int i = lane; i < rows * CW; i += 32) {
-        const int r = i / CW, c = cbase + (i % CW);
-        if (c < Cout) out[(row0 + r) * Cout + c] = apply_epilogue(acc[i], c, row0 + r, Cout, ep);
-    }
-}
-
-template <int NT>
-static int launch_tc(const float* in, const void* wf, const uint16_t* seg, const uint32_t* entries, float* out,
-                     int64_t n_out, int Cin, int Cout, int K, int TM, const insmos_epilogue_t& ep, cudaStream_t st) {
-    const int KS = (Cin + 7) / 8, NT8 = (Cout + 7) / 8;
-    const int groups = (NT8 + NT - 1) / NT;
-    const size_t smem = sizeof(float) * (size_t)MMA_WARPS * TM * NT * 8 + sizeof(int) * (size_t)MMA_WARPS * (K + 1);
-    if (smem > 220 * 1024) return INSMOS_ERR_UNSUPPORTED;
-    static thread_local insmos_smem_cfg_t configured;
-    INSMOS_CHECK_CUDA(insmos_ensure_smem(k_spconv_tc<NT>, smem, configured));
-    const int64_t n_tiles = ceil_div64(n_out, TM);
-    const int64_t warps = n_tiles * groups;
-    k_spconv_tc<NT><<<(unsigned)ceil_div64(warps, MMA_WARPS), MMA_WARPS * 32, smem, st>>>(
-        in, (const uint4*)wf, seg, entries, out, n_out, n_tiles, groups, Cin, Cout, K, TM, KS, NT8, ep);
-    INSMOS_CHECK_LAUNCH("k_spconv_tc");
-    return INSMOS_OK;
-}
-
-extern "C" int insmos_sparse_conv_fwd_tc(const float* in, int64_t n_in, int32_t Cin,
-                                         const void* wfrag, int32_t K, int32_t Cout,
-                                         const uint16_t* seg, const uint32_t* entries, int32_t TM,
-                                         float* out, int64_t n_out,
-                                         const insmos_epilogue_t* ep_in, void* stream) {
-    if ((n_in > 0 && !in) || !wfrag || !seg || !entries || (n_out > 0 && !out) || Cin <= 0 || Cout <= 0 || K <= 0 || n_out < 0 || n_in < 0)
-        return INSMOS_ERR_INVALID_ARG;
-    if (TM != 16 && TM != 32 && TM != 64 && TM != 128) return INSMOS_ERR_INVALID_ARG;
-    if (n_in > (int64_t)INSMOS_ROW_MASK + 1) return INSMOS_ERR_UNSUPPORTED;
-    insmos_epilogue_t ep = {nullptr, nullptr, nullptr, nullptr, 0};
-    if (ep_in) ep = *ep_in;
-    if (ep.scale && !ep.shift) return INSMOS_ERR_INVALID_ARG;
-    if (n_out == 0) return INSMOS_OK;
-    const int NT8 = (Cout + 7) / 8;
-    const int64_t n_tiles = ceil_div64(n_out, TM);
-    // two n-tiles per warp halve the redundant A gathers; only when that still leaves thousands of warps
-    if (NT8 % 2 == 0 && n_tiles * (NT8 / 2) >= 4096)
-        return launch_tc<2>(in, wfrag, seg, entries, out, n_out, Cin, Cout, K, TM, ep, (cudaStream_t)stream);
-    return launch_tc<1>(in, wfrag, seg, entries, out, n_out, Cin, Cout, K, TM, ep, (cudaStream_t)stream);
-}
-
-#endif  // v2
-
 extern "C" int insmos_sparse_conv_fwd(const float* in, int64_t n_in, int32_t Cin,
                                       const float* weight, int32_t K, int32_t Cout,
                                       const uint16_t* seg, const uint32_t* entries, int32_t TM,

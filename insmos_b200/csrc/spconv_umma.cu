@@ -44,251 +44,11 @@ __device__ __forceinline__ float um_epilogue(float v, int c, int64_t row, int Co
     return v;
 }
 
-template <int S>                                                     // pipeline stages = producer groups (2 or 4)
-__global__ void __launch_bounds__(UM_THREADS)
-k_spconv_umma(UmArgs p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic only: stays LDS/STS
-    const int K = p.K, TM = p.TM, G = p.G, NB = p.NB, Cin = p.Cin;
-    const int b_bytes = NB * 128;                                    // one [NB x 32] weight image
-    const int stage_bytes = 2 * UM_A_BYTES + 2 * b_bytes;
-    int* nbr = reinterpret_cast<int*>(smem + (size_t)S * stage_bytes);   // [K][128]: in_row + 1, 0 = absent
-    int* klist = nbr + K * UM_BM;                                    // [K] offsets with pairs in this super-tile
-    int* meta = klist + K;                                           // [0] = number of active offsets
-    uint64_t* bars = reinterpret_cast<uint64_t*>(meta + 2 + ((K * (UM_BM + 1)) & 1));   // 8-byte aligned: full[], empty[], accumulator ready
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * UM_MAX_STAGES + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t stile = blockIdx.x / p.nsplit;
-    const int split = (int)(blockIdx.x - stile * p.nsplit);
-    const int n0 = split * NB;
-    const int64_t tile0 = stile * G;
-    const int ntile = (int)((p.n_tiles - tile0) < G ? (p.n_tiles - tile0) : G);
-    // nacc TMEM accumulators used round-robin over the chunks and summed (fp32, round-to-nearest) in the epilogue: the
-    // tensor core truncates when it adds a product into the accumulator, so a single accumulator drifts by ~0.5 ulp
-    // per MMA (measured 5e-5 on O(1) outputs after 27 offsets x 64 channels); nacc chains are nacc x shorter.
-    const int nacc = p.nacc;
-    int tmem_cols = 32;                                              // power of two >= 32
-    while (tmem_cols < NB * nacc) tmem_cols <<= 1;
-
-    if (tid == 0) {
-        for (int s = 0; s < S; ++s) {
-            mbar_init(smem_u32(bars + s), UM_PROD_WARPS / S + 1);        // one arrive per warp of the stage's group + the TMA expect_tx
-            mbar_init(smem_u32(bars + UM_MAX_STAGES + s), 1);            // released by tcgen05.commit
-        }
-        mbar_init(smem_u32(bars + 2 * UM_MAX_STAGES), 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == UM_PROD_WARPS + 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    // ---- dense neighbour table of the super-tile from the bucketed rule book
-    for (int i = tid; i < K * UM_BM; i += UM_THREADS) nbr[i] = 0;
-    __syncthreads();
-    for (int b = tid; b < G * K; b += UM_THREADS) {
-        const int gi = b / K, k = b - gi * K;
-        if (gi < ntile) {
-            const uint16_t* tseg = p.seg + (tile0 + gi) * (K + 1);
-            const int s0 = tseg[k], s1 = tseg[k + 1];
-            const uint32_t* tent = p.entries + (tile0 + gi) * (int64_t)TM * K;
-            for (int e = s0; e < s1; ++e) {
-                const uint32_t ent = __ldg(tent + e);
-                nbr[k * UM_BM + gi * TM + (int)(ent >> INSMOS_ROW_BITS)] = (int)(ent & INSMOS_ROW_MASK) + 1;
-            }
-        }
-    }
-    if (warp == 0) {                                                 // ordered list of non-empty offsets
-        int cnt = 0;
-        for (int k0 = 0; k0 < K; k0 += 32) {
-            const int k = k0 + lane;
-            int tot = 0;
-            if (k < K)
-                for (int gi = 0; gi < ntile; ++gi) {
-                    const uint16_t* tseg = p.seg + (tile0 + gi) * (K + 1);
-                    tot += (int)tseg[k + 1] - (int)tseg[k];
-                }
-            const unsigned bal = __ballot_sync(0xffffffffu, tot > 0);
-            if (tot > 0) klist[cnt + __popc(bal & ((1u << lane) - 1u))] = k;
-            cnt += __popc(bal);
-        }
-        if (lane == 0) meta[0] = cnt;
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-    const int nact = meta[0];
-    const int cchunks = p.cchunks;
-    const int nchunks = nact * cchunks;
-
-    if (warp < UM_PROD_WARPS) {
-        // ---------------- gather producers ----------------
-        // The S stages are owned by S producer GROUPS of 8/S warps: group g fills stage g for the chunks c = g, g+S, ...
-        // A thread's fence.proxy.async waits for ALL its outstanding loads (ncu: the fence was the top stall when a
-        // thread prefetched the next chunk into registers), so the overlap of gather latency with split/store work
-        // has to come from different warps working on different stages.
-        constexpr int wg = UM_PROD_WARPS / S;                            // warps per group
-        constexpr int gthreads = wg * 32;
-        constexpr int rstep = gthreads >> 3;                             // 8 lanes per row: rows rb, rb + rstep, ...
-        constexpr int NR = UM_BM / rstep;                                // rows per thread and chunk: all gathers in flight at once
-        const int grp = warp / wg;
-        const int gt = tid - grp * gthreads;                             // thread index inside the group
-        const int q = gt & 7;                                            // 16-byte chunk of the 128-byte row image
-        const int rb = gt >> 3;
-        const bool vec = (Cin & 3) == 0;
-        const float* __restrict__ in = p.in;
-        uint8_t* a_hi = smem + (size_t)grp * stage_bytes;
-        uint8_t* a_lo = a_hi + UM_A_BYTES;
-        const uint32_t bar_full = smem_u32(bars + grp), bar_empty = smem_u32(bars + UM_MAX_STAGES + grp);
-        int kidx = 0, kc = grp;                                          // chunk c = kidx * cchunks + kc
-        while (kc >= cchunks) { kc -= cchunks; ++kidx; }
-        uint32_t ph = 0;
-        for (int c = grp; c < nchunks; c += S) {
-            const int k = klist[kidx];
-            const int c0 = kc * UM_BK + 4 * q;
-            const int cw = min(UM_BK, Cin - kc * UM_BK);                 // channels of this chunk
-            const bool wr = q < 2 * ((cw + 7) >> 3);                     // 16-byte chunks the issued K-steps read
-            const int* nb = nbr + k * UM_BM;
-            {
-                float4 v[NR];
-#pragma unroll
-                for (int i = 0; i < NR; ++i) {
-                    const int r = rb + i * rstep;
-                    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const int src = nb[r];
-                    if (src > 0 && c0 < Cin) {
-                        const float* x = in + (size_t)(src - 1) * Cin + c0;
-                        if (vec) v[i] = __ldg(reinterpret_cast<const float4*>(x));
-                        else {
-                            v[i].x = __ldg(x);
-                            if (c0 + 1 < Cin) v[i].y = __ldg(x + 1);
-                            if (c0 + 2 < Cin) v[i].z = __ldg(x + 2);
-                            if (c0 + 3 < Cin) v[i].w = __ldg(x + 3);
-                        }
-                    }
-                }
-                mbar_wait(bar_empty, ph ^ 1u);                           // stage free? (the gathers are already in flight)
-                if (wr) {
-#pragma unroll
-                    for (int i = 0; i < NR; ++i) {
-                        const int r = rb + i * rstep;
-                        float4 h, l;
-                        split_rn(v[i].x, h.x, l.x); split_rn(v[i].y, h.y, l.y);
-                        split_rn(v[i].z, h.z, l.z); split_rn(v[i].w, h.w, l.w);
-                        const int off = r * 128 + ((q ^ (r & 7)) << 4);
-                        *reinterpret_cast<float4*>(a_hi + off) = h;
-                        *reinterpret_cast<float4*>(a_lo + off) = l;
-                    }
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_full);                        // one arrival per warp
-            ph ^= 1u;
-            kc += S;
-            while (kc >= cchunks) { kc -= cchunks; ++kidx; }
-        }
-        // ---------------- epilogue: TMEM -> registers -> BN / residual / ReLU -> global ----------------
-        if (nchunks > 0) {
-            mbar_wait(smem_u32(bars + 2 * UM_MAX_STAGES), 0);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        const int halves = (NB % 32) == 0 ? 2 : 1;                       // warps 4-7 take the upper half of the columns
-        const int hcols = NB / halves;
-        const int half = warp >> 2;
-        if (half < halves) {
-            const int r = (warp & 3) * 32 + lane;                        // TMEM lane = tile row
-            const int64_t row = tile0 * TM + r;
-            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * hcols);
-#pragma unroll 1
-            for (int cb = 0; cb < hcols; cb += 16) {
-                uint32_t rr[16];
-                if (nchunks > 0) tmem_ld16(taddr + (uint32_t)cb, rr);
-                else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) rr[j] = 0u;
-                }
-                for (int a = 1; a < nacc && a < nchunks; ++a) {          // accumulators that received at least one chunk
-                    uint32_t r2[16];
-                    tmem_ld16(taddr + (uint32_t)(a * NB + cb), r2);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint(__uint_as_float(rr[j]) + __uint_as_float(r2[j]));
-                }
-                if (row < p.n_out) {
-                    const int cbase = n0 + half * hcols + cb;
-                    float* dst = p.out + row * p.Cout + cbase;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float4 o;
-                        o.x = um_epilogue(__uint_as_float(rr[4 * j + 0]), cbase + 4 * j + 0, row, p.Cout, p.ep);
-                        o.y = um_epilogue(__uint_as_float(rr[4 * j + 1]), cbase + 4 * j + 1, row, p.Cout, p.ep);
-                        o.z = um_epilogue(__uint_as_float(rr[4 * j + 2]), cbase + 4 * j + 2, row, p.Cout, p.ep);
-                        o.w = um_epilogue(__uint_as_float(rr[4 * j + 3]), cbase + 4 * j + 3, row, p.Cout, p.ep);
-                        *reinterpret_cast<float4*>(dst + 4 * j) = o;
-                    }
-                }
-            }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    } else if (warp == UM_PROD_WARPS) {
-        // ---------------- TMA: weight images ----------------
-        if (lane == 0) {
-            const size_t img_floats = (size_t)p.Cout * 32;               // one [Cout x 32] image (hi or lo)
-            int s = 0, kidx = 0, kc = 0;
-            uint32_t ph = 0;
-            for (int c = 0; c < nchunks; ++c) {
-                const int k = klist[kidx];
-                mbar_wait(smem_u32(bars + UM_MAX_STAGES + s), ph ^ 1u);
-                const float* hi = p.wimg + ((size_t)k * cchunks + kc) * 2 * img_floats + (size_t)n0 * 32;
-                const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes + 2 * UM_A_BYTES);
-                mbar_arrive_expect_tx(smem_u32(bars + s), 2u * (uint32_t)b_bytes);
-                tma_bulk_g2s(dst, hi, (uint32_t)b_bytes, smem_u32(bars + s));
-                tma_bulk_g2s(dst + (uint32_t)b_bytes, hi + img_floats, (uint32_t)b_bytes, smem_u32(bars + s));
-                if (++s == S) { s = 0; ph ^= 1u; }
-                if (++kc == cchunks) { kc = 0; ++kidx; }
-            }
-        }
-    } else {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_tf32_m128(NB);
-            int s = 0, kc = 0, acc = 0;
-            uint32_t ph = 0;
-            for (int c = 0; c < nchunks; ++c) {
-                mbar_wait(smem_u32(bars + s), ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint64_t a_hi = umma_desc_sw128(base), a_lo = umma_desc_sw128(base + UM_A_BYTES);
-                const uint64_t b_hi = umma_desc_sw128(base + 2 * UM_A_BYTES), b_lo = umma_desc_sw128(base + 2 * UM_A_BYTES + b_bytes);
-                const int cw = min(UM_BK, Cin - kc * UM_BK);
-                const int ksteps = (cw + 7) >> 3;
-                const uint32_t dacc = tmem_base + (uint32_t)(acc * NB);
-                for (int j = 0; j < ksteps; ++j) {
-                    const uint64_t adv = (uint64_t)(j * 2);                 // 32 bytes per K-step, in 16-byte units
-                    umma_tf32(dacc, a_lo + adv, b_hi + adv, idesc, (c >= nacc || j != 0) ? 1u : 0u);
-                    umma_tf32(dacc, a_hi + adv, b_lo + adv, idesc, 1u);
-                    umma_tf32(dacc, a_hi + adv, b_hi + adv, idesc, 1u);
-                }
-                umma_commit(smem_u32(bars + UM_MAX_STAGES + s));            // stage reusable once these MMAs retire
-                if (++s == S) { s = 0; ph ^= 1u; }
-                if (++kc == cchunks) kc = 0;
-                if (++acc == nacc) acc = 0;
-            }
-            if (nchunks > 0) umma_commit(smem_u32(bars + 2 * UM_MAX_STAGES));   // accumulator complete
-        }
-    }
-    __syncthreads();
-    if (warp == UM_PROD_WARPS + 1) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // TS variant: the gathered A operand goes to TENSOR MEMORY instead of shared memory.
 // Measured on B200 (tools/micro/umma_rate.cu, profiles/r01_umma_notes.md): a tcgen05.mma kind::tf32 M=128 K=8 occupies
 // the tensor pipe for ~75-86 cycles whatever N <= 128 is, i.e. ~1000 cycles per 32-channel chunk with the 3xTF32
-// products.  In the SS kernel above the MMA operand reads (6-8 KB per instruction), the producers' 32 KB of stores and
+// products.  In the first (SS, removed) kernel the MMA operand reads (6-8 KB per instruction), the producers' 32 KB of stores and
 // the TMA's weight tiles share the 128 B/clk shared-memory port and a chunk takes ~2000 cycles.  Here the producers
 // write the TF32 hi/lo rows straight into TMEM with tcgen05.st (thread = tile row = TMEM lane) and only the weight
 // tile is read from shared memory.  tcgen05.wait::st does not wait for global loads, so the next chunk's gathers stay
@@ -617,7 +377,7 @@ __global__ void k_umma_prep_weights(const float* __restrict__ w, int K, int Cin,
 }
 
 static bool umma_shape_ok(int32_t K, int32_t Cin, int32_t Cout) {
-    return K > 0 && K <= 128 && Cin > 0 && Cin <= 1024 && Cout >= 16 && Cout <= 256 && (Cout % 16) == 0;
+    return K > 0 && K <= 128 && Cin > 0 && Cin <= 1024 && Cout >= 16 && Cout <= 128 && (Cout % 16) == 0;
 }
 
 extern "C" int64_t insmos_conv_wimg_elems(int32_t K, int32_t Cin, int32_t Cout) {
@@ -704,48 +464,13 @@ extern "C" int insmos_sparse_conv_fwd_umma(const float* in, int64_t n_in, int32_
     if (ep_in) a.ep = *ep_in;
     if (a.ep.scale && !a.ep.shift) return INSMOS_ERR_INVALID_ARG;
     if (n_out == 0) return INSMOS_OK;
-    static const bool force_ss = getenv("INSMOS_UMMA_SS") != nullptr;     // A/B switch: operands from shared memory
-    if (!force_ss && Cout <= 128) {
-        UtArgs t;
-        t.in = in; t.wimg = wimg; t.seg = seg; t.entries = entries; t.out = out;
-        t.n_out = n_out; t.n_tiles = a.n_tiles;
-        t.Cin = Cin; t.Cout = Cout; t.K = K; t.TM = TM; t.G = a.G; t.cchunks = a.cchunks; t.ep = a.ep;
-        t.dense_H = 0; t.dense_W = 0;
-        const int rc = launch_umma_ts(t, workspace, workspace_bytes, (cudaStream_t)stream);
-        if (rc != INSMOS_ERR_UNSUPPORTED) return rc;
-    }
-    const int64_t stiles = ceil_div64(a.n_tiles, a.G);
-    // split the output channels over CTAs while the layer has too few super-tiles to fill 148 SMs (the gather is
-    // repeated per split, the MMA work is not)
-    int nsplit = 1;
-    while (stiles * nsplit < 120 && Cout / (nsplit * 2) >= 32 && (Cout / (nsplit * 2)) % 16 == 0) nsplit *= 2;
-    if (const char* e = getenv("INSMOS_UMMA_NSPLIT")) {
-        const int v = atoi(e);
-        if (v >= 1 && Cout % v == 0 && (Cout / v) % 16 == 0) nsplit = v;
-    }
-    a.nsplit = nsplit; a.NB = Cout / nsplit;
-    if (a.NB > 128) { a.nsplit = Cout / 128; a.NB = 128; if (Cout % 128) return INSMOS_ERR_UNSUPPORTED; }
-    const size_t stage_bytes = 2 * (size_t)UM_A_BYTES + 2 * (size_t)a.NB * 128;
-    const size_t fixed = 1024 + sizeof(int) * ((size_t)K * UM_BM + K + 2) + 8 * (2 * UM_MAX_STAGES + 1) + 8 + 16;
-    int stages = UM_MAX_STAGES;                                       // 2 or 4: the 8 producer warps are split into `stages` groups
-    if (fixed + stages * stage_bytes > 220 * 1024) stages = 2;
-    // many CTAs: two resident CTAs per SM (each with a 2-stage ring) overlap each other's gather latency
-    if (stiles * a.nsplit > 148 && fixed + 2 * stage_bytes <= 112 * 1024) stages = 2;
-    if (const char* e = getenv("INSMOS_UMMA_STAGES")) { const int v = atoi(e); if (v == 2 || v == 4) stages = v; }
-    const size_t smem = fixed + stages * stage_bytes;
-    if (smem > 227 * 1024) return INSMOS_ERR_UNSUPPORTED;
-    a.stages = stages;
-    const int ctas_per_sm = (int)((227 * 1024) / (smem + 1024)) < 1 ? 1 : (int)((227 * 1024) / (smem + 1024));
-    int nacc = 4;                                                     // TMEM: 512 columns per SM shared by the resident CTAs
-    while (nacc > 1 && a.NB * nacc * ctas_per_sm > 512) nacc /= 2;
-    if (const char* e = getenv("INSMOS_UMMA_NACC")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && a.NB * v <= 512) nacc = v; }
-    a.nacc = nacc;
-    static thread_local insmos_smem_cfg_t configured[2];
-    auto kern = stages == 4 ? k_spconv_umma<4> : k_spconv_umma<2>;
-    INSMOS_CHECK_CUDA(insmos_ensure_smem(kern, smem, configured[stages == 4]));
-    kern<<<(unsigned)(stiles * a.nsplit), UM_THREADS, smem, (cudaStream_t)stream>>>(a);
-    INSMOS_CHECK_LAUNCH("k_spconv_umma");
-    return INSMOS_OK;
+    if (Cout > 128) return INSMOS_ERR_UNSUPPORTED;
+    UtArgs t;
+    t.in = in; t.wimg = wimg; t.seg = seg; t.entries = entries; t.out = out;
+    t.n_out = n_out; t.n_tiles = a.n_tiles;
+    t.Cin = Cin; t.Cout = Cout; t.K = K; t.TM = TM; t.G = a.G; t.cchunks = a.cchunks; t.ep = a.ep;
+    t.dense_H = 0; t.dense_W = 0;
+    return launch_umma_ts(t, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 // Dense 3x3 / pad 1 image convolution (BEV backbone, base_bev_backbone.py:33-82 with BatchNorm folded) through the same

@@ -4,7 +4,7 @@ Mirrors models/backbones_2d/{height_compression.py:8-33, base_bev_backbone.py:9-
 center_head.py:29-98,251-276} (module tree / state_dict keys identical).  Inference path (eval mode):
 the whole head runs channels-last on this repository's tensor-core kernels -- sparse->dense scatter straight
 into NHWC, the 3x3 convs and the 2x2 transposed conv as 3xTF32 implicit GEMMs with BatchNorm folded into the
-weights and ReLU in the epilogue (insmos_conv2d_nhwc_tc), the two 1x1 heads as one fused linear kernel, and
+weights and ReLU in the epilogue (insmos_conv2d_nhwc_umma / _tcgen05), the two 1x1 heads as one fused linear kernel, and
 decode + sigmoid + class max in one kernel.  Training mode falls back to the plain torch modules.
 """
 import numpy as np

@@ -437,8 +437,13 @@ def fma_eligible(K, Cin, Cout):
     return Cin % 8 == 0 and 8 <= Cin <= 256 and Cout in (8, 16, 32)
 
 
+def tc_eligible(K, Cin, Cout, TM):
+    """shapes of the mma.sync kernel (conv_tc.cu): compile-time Cin in {8,16,24,32,48}, Cout < 64 (any: n-tiles are padded)."""
+    return Cin in (8, 16, 24, 32, 48) and Cout < 64 and K <= 127 and TM * K < 65536
+
+
 def umma_eligible(K, Cin, Cout):
-    return Cout % 16 == 0 and 16 <= Cout <= 256 and K <= 128 and (Cout <= 128 or Cout % 128 == 0)
+    return Cout % 16 == 0 and 16 <= Cout <= 128 and K <= 128
 
 
 def prepared_weight_images(weight):
@@ -489,7 +494,7 @@ def sparse_conv(feat, weight, rb, scale=None, shift=None, bias=None, residual=No
     out = torch.empty((rb.n_out, Cout), dtype=F32, device=feat.device)
     ep, keep = _epilogue(scale, shift, bias, residual, relu)
     if algo == 0:
-        algo = DEFAULT_CONV_ALGO if Cout % 4 == 0 else 2
+        algo = DEFAULT_CONV_ALGO
         if algo == 2 and Cin < 8 and Cout % 4 == 0 and Cout <= 16:
             algo = 1          # 1..7 input channels: a tensor-core k-step would be mostly padding; fp32 thread-per-pair
         if (algo == 2 and USE_UMMA and Cin >= UMMA_MIN_CIN and Cout >= UMMA_MIN_COUT and K <= UMMA_MAX_K
@@ -497,6 +502,9 @@ def sparse_conv(feat, weight, rb, scale=None, shift=None, bias=None, residual=No
             algo = 4
         if algo == 2 and USE_FMA and fma_eligible(K, Cin, Cout) and rb.TM * K < 65536:
             algo = 5
+        if algo == 2 and not tc_eligible(K, Cin, Cout, rb.TM):
+            # off the tuned shapes: tcgen05 kernel when it applies (wide layers with many offsets), else the general SIMT kernel
+            algo = 4 if (USE_UMMA and umma_eligible(K, Cin, Cout) and Cin % 8 == 0 and Cin >= 16) else 3
     wf = prepared_weights(weight) if algo == 2 else None
     if _lib.PROFILE is not None:          # algorithmic bytes / flops of this launch (SURVEY 8d formula)
         P = rb.num_pairs
@@ -626,8 +634,8 @@ def center_decode(cls, box, out_size_factor, vx, vy, x_min, y_min, hw=None):
     return boxes, scores, labels
 
 
-# dense BEV conv implementation: "umma" (3x3 convs through the TMEM-operand kernel of spconv_umma.cu, the rest as "tcgen05"),
-# "tcgen05" (UTCHMMA + TMEM + TMA, operands in shared memory, bev_tcgen05.cu) or "mma" (mma.sync, bev.cu)
+# dense BEV conv implementation: "umma" (3x3 convs through the TMEM-operand kernel of spconv_umma.cu, the rest as "tcgen05")
+# or "tcgen05" (UTCHMMA + TMEM + TMA, operands in shared memory, bev_tcgen05.cu)
 BEV_IMPL = _os.environ.get("INSMOS_BEV_IMPL", "umma")
 _WIMG_CACHE = {}
 
@@ -665,7 +673,7 @@ def conv2d_nhwc(x, H, W, weight, mode, bias=None, relu=False, impl=None):
         img = bev_weight_images(weight)
         call("insmos_conv2d_nhwc_tcgen05", _p(x), H, W, Cin, _p(img), mode, Cout, _p(bias), 1 if relu else 0, _p(out), _stream())
     else:
-        call("insmos_conv2d_nhwc_tc", _p(x), H, W, Cin, _p(weight), mode, Cout, _p(bias), 1 if relu else 0, _p(out), _stream())
+        raise ValueError("conv2d_nhwc: unknown implementation %r (umma | tcgen05)" % (which,))
     return out
 
 

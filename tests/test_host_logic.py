@@ -22,7 +22,8 @@ def test_tcgen05_eligibility_table():
     assert not ops.umma_eligible(27, 64, 8)            # N must be a multiple of 16
     assert not ops.umma_eligible(27, 64, 24)
     assert not ops.umma_eligible(200, 64, 64)          # neighbour table limited to 128 offsets
-    assert ops.umma_eligible(27, 64, 256) and not ops.umma_eligible(27, 64, 192)
+    assert not ops.umma_eligible(27, 64, 256) and not ops.umma_eligible(27, 64, 192)      # one TMEM tile: Cout <= 128
+    assert ops.tc_eligible(81, 48, 32, 128) and not ops.tc_eligible(81, 19, 16, 64) and not ops.tc_eligible(27, 64, 64, 64)
 
 
 def test_kernel_count_table_names_exist_in_the_abi():

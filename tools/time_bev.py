@@ -12,7 +12,7 @@ for Cin, Cout, mode in ((256, 128, 0), (128, 128, 0), (128, 256, 2)):
     w = torch.randn(taps, Cin, Cout, device=dev) / (taps * Cin) ** 0.5
     b = torch.randn(Cout, device=dev)
     ref = None
-    for impl in ("mma", "tcgen05", "umma"):
+    for impl in ("tcgen05", "umma"):
         for _ in range(3):
             out = ops.conv2d_nhwc(x, H, W, w, mode, bias=b, relu=True, impl=impl)
         torch.cuda.synchronize()
