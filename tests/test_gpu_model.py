@@ -154,18 +154,26 @@ def test_fresh_input_matches_oracle_graph(cuda):
 
 
 def test_sparse_conv_algorithms_agree_in_model(cuda):
-    """same forward with the tensor-core 3xTF32 kernels forced == default exact-fp32 FFMA path within 1e-3"""
+    """the default forward (3xTF32 mma.sync / tcgen05 kernels per layer) == the same forward with EVERY sparse convolution on
+    the general exact-fp32 SIMT kernel, and == with the narrow layers on the exact-fp32 FFMA kernel, within 1e-3"""
     meta, shapes, sd, pts, gold = golden_util.load("small_nodet")
     net = _net(cuda, sd)
     from insmos_b200 import ops
     _, _, logits_auto = _run(net, pts, cuda)
     orig = ops.sparse_conv
     try:
-        ops.sparse_conv = lambda *a, **k: orig(*a, **{**k, "algo": 2})
+        ops.sparse_conv = lambda *a, **k: orig(*a, **{**k, "algo": 3})
         _, _, logits_simt = _run(net, pts, cuda)
+
+        def narrow_fma(feat, weight, rb, **k):
+            K, Cin, Cout = weight.shape
+            return orig(feat, weight, rb, **{**k, "algo": 5 if ops.fma_eligible(K, Cin, Cout) and rb.TM * K < 65536 else 0})
+        ops.sparse_conv = narrow_fma
+        _, _, logits_fma = _run(net, pts, cuda)
     finally:
         ops.sparse_conv = orig
     assert (logits_auto - logits_simt).abs().max().item() < LOGIT_ATOL
+    assert (logits_fma - logits_simt).abs().max().item() < LOGIT_ATOL
 
 
 def test_reference_op_sequence_through_shims(cuda):
