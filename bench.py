@@ -194,7 +194,7 @@ def run_c4(args, device, out_stream):
             ("2x2x2x1 ts1->ts2", c2s, cs, [2, 2, 2, 1], [1, 1, 1, 1], None, [(8, 8)]),
             ("3x3x3x3 ts2", c2s, c2s, [3, 3, 3, 3], [2, 2, 2, 1], 2, [(8, 16), (16, 16)])):
         spec = ops.spec_me_cube(ksize, ist)
-        ms, rb = timed(lambda: ops.build_rulebook(out_set, in_set, spec, xstep=xs), reps)
+        ms, rb = timed(lambda: ops.build_rulebook(out_set, in_set, spec, xstep=xs, step=tuple(ist)), reps)
         P, K = rb.num_pairs, int(np.prod(ksize))
         b = 4 * out_set.ncol * out_set.n + 8 * P
         rows.append({"op": "rulebook " + name, "ms": round(ms, 4), "n_out": out_set.n, "K": K, "pairs": P,

@@ -178,6 +178,23 @@ int insmos_rulebook_build_xb(const int32_t* out_coords, int64_t n_out,
                              const insmos_mapspec_t* spec, int32_t TM,
                              uint16_t* seg, uint32_t* entries, unsigned long long* pair_count, void* stream);
 
+/* LEAF GRID of a coordinate set: the same voxels stored as a sparse grid of 4x4x4 (x1 in time) leaves -- a hash table of
+ * leaf keys plus, per slot, the dense 64-entry array of the voxels' rows.  step[d] = lattice step of the set in dimension d
+ * (tensor stride of a MinkowskiEngine level, 1 for spconv indices).  grid = insmos_leafgrid_bytes(cap) bytes of scratch,
+ * cap = insmos_leafgrid_capacity(n).  insmos_rulebook_build_lg builds the same map as insmos_rulebook_build (bit-identical
+ * seg / entries) for an affine spec (mode 0, q = 1, e[d] == step[d]): per output row at most 24 leaf probes, then every
+ * kernel offset is one indexed load.  Inputs with too many leaves for the bounded probing (isolated voxels) raise an
+ * overflow word inside the grid and the builder falls back to voxel-table probes on the device. */
+int64_t insmos_leafgrid_capacity(int64_t n);
+int64_t insmos_leafgrid_bytes(int64_t cap);
+int insmos_leafgrid_build(const int32_t* coords, int64_t n, int32_t ncol, const int32_t* step,
+                          void* grid, int64_t cap, void* stream);
+int insmos_rulebook_build_lg(const int32_t* out_coords, int64_t n_out,
+                             const insmos_slot_t* in_table, int64_t in_cap,
+                             const void* grid, int64_t grid_cap, const int32_t* step,
+                             const insmos_mapspec_t* spec, int32_t TM,
+                             uint16_t* seg, uint32_t* entries, unsigned long long* pair_count, void* stream);
+
 /* Transposed (MinkowskiConvolutionTranspose, kernel == stride) map built without hash probes: the only pair of fine row
  * i is (offset of i inside its coarse cell, parent[i]) where parent is the inverse map insmos_unique_coords(q) returned
  * when the coarse set was made (ME derives the same map by swapping the strided one: minkunet.py:96-125).  `spec` is the

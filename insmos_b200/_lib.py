@@ -52,6 +52,10 @@ PROTOTYPES = {
     "insmos_xblock_capacity": (_I64, [_I64]),
     "insmos_xblock_build": (C.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P]),
     "insmos_rulebook_build_xb": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, C.POINTER(MapSpec), _I32, _P, _P, _P, _P]),
+    "insmos_leafgrid_capacity": (_I64, [_I64]),
+    "insmos_leafgrid_bytes": (_I64, [_I64]),
+    "insmos_leafgrid_build": (C.c_int, [_P, _I64, _I32, C.POINTER(_I32), _P, _I64, _P]),
+    "insmos_rulebook_build_lg": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, C.POINTER(_I32), C.POINTER(MapSpec), _I32, _P, _P, _P, _P]),
     "insmos_rulebook_build_up": (C.c_int, [_P, _I64, _P, C.POINTER(MapSpec), _I32, _P, _P, _P, _P]),
     "insmos_sparse_conv_fwd": (C.c_int, [_P, _I64, _I32, _P, _I32, _I32, _P, _P, _I32, _P, _I64,
                                          C.POINTER(Epilogue), _I32, _P]),
@@ -138,7 +142,7 @@ KERNELS_PER_CALL = {
     "insmos_affine_act": 1, "insmos_concat2": 1, "insmos_pairsum_add": 1, "insmos_gather_rows": 1,
     "insmos_segment_mean": 2, "insmos_build_current_points": 1, "insmos_dense_scatter": 1, "insmos_center_decode": 1,
     "insmos_nms_rotated": 2, "insmos_point_instance_ids": 3, "insmos_nms_rotated_pairs": 4, "insmos_boxes_to_voxel_units": 1, "insmos_box_membership": 3,
-    "insmos_xblock_build": 2, "insmos_rulebook_build_xb": 1, "insmos_rulebook_build_up": 1,
+    "insmos_xblock_build": 2, "insmos_leafgrid_build": 1, "insmos_rulebook_build_lg": 1, "insmos_rulebook_build_xb": 1, "insmos_rulebook_build_up": 1,
     "insmos_sparse_conv_fwd_umma": 1, "insmos_conv2d_nhwc_umma": 1, "insmos_conv2d_nhwc_tcgen05": 1,
     "insmos_conv_prep_weights_umma": 1, "insmos_bev_prep_weights_tcgen05": 1, "insmos_dense_scatter_nhwc": 1,
 }

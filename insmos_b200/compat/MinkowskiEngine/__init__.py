@@ -63,7 +63,7 @@ class CoordinateManager:
             parent = self.parents.get((out_key, in_key)) if kind == "up" else None
             # every set of this manager holds coordinates that are multiples of its tensor stride -> x-block probing
             rb = ops.build_rulebook(self.sets[out_key], self.sets[in_key], spec, parent=parent,
-                                    xstep=in_key[0] if kind == "conv" else None)
+                                    xstep=in_key[0] if kind == "conv" else None, step=in_key if kind == "conv" else None)
             self.rulebooks[k] = rb
         return rb
 

@@ -17,7 +17,7 @@ class IndiceData:
     def forward_rulebook(self):
         if self._fwd is None:
             spec = ops.spec_sp_subm(self.ksize) if self.subm else ops.spec_sp_conv(self.ksize, self.stride, self.padding)
-            self._fwd = ops.build_rulebook(self.out_set, self.in_set, spec)
+            self._fwd = ops.build_rulebook(self.out_set, self.in_set, spec, step=(1, 1, 1))
         return self._fwd
 
     def inverse_rulebook(self):

@@ -103,13 +103,106 @@ __device__ __forceinline__ int4 xblock_find(const XBlockSlot* __restrict__ table
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// LEAF GRID.  ncu of the probe loop (profiles/r01_fwd_v7_summary.txt, r01_umma_notes.md section 6): 54 % issue active and the
+// same ~100 G probes/s on a 2 MB table as on a 32 MB one -- the build is bound by the INSTRUCTIONS of 81-125 independent
+// hash probes per row (hash, 64-bit compare, divergent linear-probe chains), not by where the slots come from.  A voxel's
+// kernel neighbourhood is spatially compact, so the input set is also stored as a sparse grid of 4 x 4 x 4 (x 1 in t) leaves:
+// a small hash table of leaf keys (8 bytes each) and, per table slot, the dense 64-entry array of the rows of the leaf's
+// voxels.  Per output row the 3 x 3 x 3 (x 3) or 5 x 5 x 5 neighbourhood touches at most 2 x 2 x 2 (x 3) = 24 leaves: ONE
+// warp iteration of parallel leaf probes, then every kernel offset is a shuffle + an indexed 4-byte load (no hash, no key
+// compare, no chain) and the loads of a row fall into the few 256-byte leaf arrays it touches.
+// Index space: coordinates of a strided level are multiples of step[d]; leaf coordinate = floor(c / step) >> lsh[d].
+struct LgGeom { int step[4]; int lsh[4]; int mb[4]; int ncand; };
+// Every key sits within LG_MAX_PROBE slots of its home slot, or the build raises the grid's overflow word and the map
+// builders ignore the grid (plain voxel-table probes): lookups are bounded and never wrong, whatever the input.
+#define LG_MAX_PROBE 64
+
+__global__ void k_leafgrid_insert(const int32_t* __restrict__ coords, int64_t n, int ncol, LgGeom g,
+                                  unsigned long long* __restrict__ keys, int32_t* __restrict__ rows, uint64_t mask,
+                                  unsigned int* __restrict__ ok_word) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t* c = coords + i * ncol;
+    int blk[4] = {0, 0, 0, 0}, loc = 0, bit = 0;
+    for (int d = 0; d < ncol - 1; ++d) {
+        const int idx = floor_div(c[1 + d], g.step[d]);
+        blk[d] = idx >> g.lsh[d];
+        loc |= (idx & ((1 << g.lsh[d]) - 1)) << bit;
+        bit += g.lsh[d];
+    }
+    const uint64_t key = pack_key(c[0], blk[0], blk[1], blk[2], blk[3]);
+    uint64_t slot = hash64(key) & mask;
+    for (int step = 0; step < LG_MAX_PROBE; ++step) {
+        unsigned long long* kp = keys + slot;
+        const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
+        bool mine = cur == key;
+        if (!mine && cur == INSMOS_EMPTY_KEY) {
+            const unsigned long long prev = atomicCAS(kp, INSMOS_EMPTY_KEY, (unsigned long long)key);
+            mine = prev == INSMOS_EMPTY_KEY || prev == key;
+        }
+        if (mine) { rows[slot * 64 + loc] = (int32_t)i; return; }
+        slot = (slot + 1) & mask;
+    }
+    *ok_word = 0u;                                               // table too crowded for bounded probing: grid unusable
+}
+__device__ __forceinline__ int lg_find(const unsigned long long* __restrict__ keys, uint64_t mask, uint64_t key) {
+    uint64_t slot = hash64(key) & mask;
+    for (int step = 0; step < LG_MAX_PROBE; ++step) {
+        const unsigned long long k = __ldg(keys + slot);
+        if (k == key) return (int)slot;
+        if (k == INSMOS_EMPTY_KEY) return -1;
+        slot = (slot + 1) & mask;
+    }
+    return -1;                                                   // every stored key is within LG_MAX_PROBE of its home slot
+}
+extern "C" int64_t insmos_leafgrid_capacity(int64_t n) {
+    // leaves <= voxels; LiDAR surfaces put ~8 voxels in a 4x4x4 leaf, so a table of >= n/2 slots runs at a load of ~0.25.
+    // Inputs with more leaves than that (isolated voxels) overflow the bounded probing and fall back to the voxel table.
+    int64_t cap = 1024;
+    while (2 * cap < n) cap <<= 1;
+    return cap;
+}
+extern "C" int64_t insmos_leafgrid_bytes(int64_t cap) { return cap <= 0 ? 0 : cap * 8 + cap * 64 * 4 + 16; }
+static int lg_geometry(int ncol, const int32_t* step, LgGeom& g) {
+    for (int d = 0; d < 4; ++d) { g.step[d] = 1; g.lsh[d] = 0; g.mb[d] = 1; }
+    const int ndim = ncol - 1;
+    if (ndim < 1 || ndim > 4 || !step) return INSMOS_ERR_INVALID_ARG;
+    for (int d = 0; d < ndim; ++d) {
+        if (step[d] < 1) return INSMOS_ERR_INVALID_ARG;
+        g.step[d] = step[d];
+        g.lsh[d] = d < 3 ? 2 : 0;                                  // 4 x 4 x 4 leaves in space, 1 in time
+    }
+    return INSMOS_OK;
+}
+extern "C" int insmos_leafgrid_build(const int32_t* coords, int64_t n, int32_t ncol, const int32_t* step,
+                                     void* grid, int64_t cap, void* stream) {
+    if (!grid || cap <= 0 || (cap & (cap - 1)) || cap > (1ll << 30) || (n > 0 && !coords) || n < 0 || ncol < 2 || ncol > 5)
+        return INSMOS_ERR_INVALID_ARG;
+    LgGeom g;
+    const int rc = lg_geometry(ncol, step, g);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    INSMOS_CHECK_CUDA(cudaMemsetAsync(grid, 0xFF, (size_t)insmos_leafgrid_bytes(cap), st));   // keys = empty, rows = -1
+    if (n > 0) {
+        unsigned long long* keys = reinterpret_cast<unsigned long long*>(grid);
+        int32_t* rows = reinterpret_cast<int32_t*>(keys + cap);
+        unsigned int* ok_word = reinterpret_cast<unsigned int*>(rows + cap * 64);      // 0xffffffff after the memset = usable
+        k_leafgrid_insert<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(coords, n, ncol, g, keys, rows, (uint64_t)(cap - 1), ok_word);
+        INSMOS_CHECK_LAUNCH("k_leafgrid_insert");
+    }
+    return INSMOS_OK;
+}
+
 __global__ void __launch_bounds__(RB_THREADS)
 k_rulebook_tiles(const int32_t* __restrict__ out_coords, int64_t n_out,
                  const insmos_slot_t* __restrict__ table, uint64_t mask,
                  insmos_mapspec_t spec, int TM,
                  uint16_t* __restrict__ seg, uint32_t* __restrict__ entries,
                  unsigned long long* pair_count, const int32_t* __restrict__ parent,
-                 const XBlockSlot* __restrict__ xtable, uint64_t xmask, int xstep) {
+                 const XBlockSlot* __restrict__ xtable, uint64_t xmask, int xstep,
+                 const unsigned long long* __restrict__ lgkeys, const int32_t* __restrict__ lgrows, uint64_t lgmask, LgGeom lg) {
     extern __shared__ __align__(16) int smem[];
     const int K = spec.K, ncol = spec.ncol, ndim = spec.ndim;
     int* nbr = smem;                                            // [TM*K] in-row or -1
@@ -118,6 +211,9 @@ k_rulebook_tiles(const int32_t* __restrict__ out_coords, int64_t n_out,
     int* kd = reinterpret_cast<int*>(rbase + TM);               // [K*4] per-offset digits/terms (slow path)
     int* tc = kd + K * 4;                                       // [TM*5] coordinates of the tile's rows
     int* hist = tc + TM * 5;                                    // [K+1]
+    int* kpk = hist + K + 1;                                    // [K] kernel digits packed one byte per dimension (leaf-grid path)
+    int* rowblk = kpk + K;                                      // [TM*4] leaf coordinate of the row's neighbourhood corner
+    unsigned* rowoff = reinterpret_cast<unsigned*>(rowblk + TM * 4);   // [TM] offset of the corner inside its leaf, one byte per dim
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = RB_THREADS / 32;
     const int64_t tile = blockIdx.x;
     const int64_t row0 = tile * TM;
@@ -138,6 +234,7 @@ k_rulebook_tiles(const int32_t* __restrict__ out_coords, int64_t n_out,
             kd[k * 4 + d] = (d < ndim && spec.mode == 0) ? spec.b[d] + term[d] : term[d];
         }
         delta[k] = packed_delta(term[0], term[1], term[2], term[3]);
+        kpk[k] = dig[0] | (dig[1] << 8) | (dig[2] << 16) | (dig[3] << 24);
         hist[k] = 0;
     }
     __syncthreads();
@@ -162,6 +259,74 @@ k_rulebook_tiles(const int32_t* __restrict__ out_coords, int64_t n_out,
         __syncthreads();
     }
 
+    // ---- phase A (leaf grid): one warp iteration of parallel leaf probes per row, then shuffle + indexed load per offset.
+    // Leaves are 4 x 4 x 4 in the (up to three) spatial dimensions and 1 in time: the unpacking below is written for that
+    // geometry (ncu of the first, generic version: the per-row set-up with four runtime divisions executed by every warp was
+    // 21 % of all instructions -- it now runs once per row in a thread-per-row pre-pass, with shifts for power-of-two steps).
+    const bool use_lg = lgkeys && fast && (*reinterpret_cast<const unsigned int*>(lgrows + (lgmask + 1) * 64) != 0u);
+    if (use_lg) {
+        for (int r = tid; r < TM; r += RB_THREADS) {
+            // low corner of the row's neighbourhood in index space: leaf coordinate + offset inside the leaf (one byte per dim)
+            const int* c = tc + r * 5;
+            int blk[4] = {0, 0, 0, 0};
+            unsigned off = 0u;
+            bool lattice = (row0 + r) < n_out && rbase[r] >= 0;
+#pragma unroll
+            for (int d = 0; d < 4; ++d)
+                if (d < ndim) {
+                    const int lo = c[1 + d] * spec.a[d] + spec.b[d];
+                    const int sh = lg.lsh[d];                            // here: log2(step) or -1
+                    const int idx = sh >= 0 ? (lo >> sh) : floor_div(lo, lg.step[d]);
+                    lattice = lattice && (idx * lg.step[d] == lo);     // off the input lattice: no neighbour can exist
+                    if (d < 3) { blk[d] = idx >> 2; off |= (unsigned)(idx & 3) << (8 * d); }
+                    else blk[d] = idx;
+                }
+            rowblk[r * 4 + 0] = blk[0]; rowblk[r * 4 + 1] = blk[1]; rowblk[r * 4 + 2] = blk[2]; rowblk[r * 4 + 3] = blk[3];
+            rowoff[r] = lattice ? off : 0xffffffffu;
+        }
+        __syncthreads();
+        int cj[4];                                               // this lane's candidate leaf (j0..j3) -- a function of the lane only
+        { int t = lane; for (int d = 0; d < 4; ++d) { cj[d] = t % lg.mb[d]; t /= lg.mb[d]; } }
+        const int s1 = lg.mb[0], s2 = lg.mb[0] * lg.mb[1], s3 = lg.mb[0] * lg.mb[1] * lg.mb[2];
+        const int Kpad = (K + 31) & ~31;
+        for (int r = warp; r < TM; r += nwarps) {
+            const bool row_ok = (row0 + r) < n_out;
+            const int* c = tc + r * 5;
+            if (row_ok && rbase[r] == -2) {                          // near the edge of the packable range: checked path, voxel table
+                for (int k = lane; k < K; k += 32) {
+                    int ci[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) if (d < ndim) ci[d] = c[1 + d] * spec.a[d] + kd[k * 4 + d];
+                    int res = -1;
+                    if (coord_in_range(c[0], ci[0], ci[1], ci[2], ci[3]))
+                        res = table_find_row(table, mask, pack_key(c[0], ci[0], ci[1], ci[2], ci[3]));
+                    nbr[r * K + k] = res;
+                    if (res >= 0) atomicAdd(&hist[k], 1);
+                }
+                continue;
+            }
+            const unsigned off = rowoff[r];
+            int myslot = -1;
+            if (off != 0xffffffffu && lane < lg.ncand) {
+                const int* b = rowblk + r * 4;
+                myslot = lg_find(lgkeys, lgmask, pack_key(c[0], b[0] + cj[0], b[1] + cj[1], b[2] + cj[2], b[3] + cj[3]));
+            }
+            for (int k = lane; k < Kpad; k += 32) {                  // all lanes take part in the shuffle
+                const unsigned v = off + (unsigned)kpk[k < K ? k : 0];   // byte d = offset in the leaf + kernel digit (< 64)
+                const unsigned t0 = v & 0x00030303u;
+                const int loc = (int)((t0 | (t0 >> 6) | (t0 >> 12)) & 0x3fu);
+                const unsigned jj = v >> 2;
+                const int cand = (int)(jj & 0x3fu) + (int)((jj >> 8) & 0x3fu) * s1 + (int)((jj >> 16) & 0x3fu) * s2 + (int)(v >> 24) * s3;
+                const int slot = __shfl_sync(0xffffffffu, myslot, cand & 31);
+                if (k < K) {
+                    int res = -1;
+                    if (slot >= 0) res = __ldg(lgrows + (size_t)slot * 64 + loc);
+                    nbr[r * K + k] = res;
+                    if (res >= 0) atomicAdd(&hist[k], 1);
+                }
+            }
+        }
+    } else
     // ---- phase A (x-block table): lanes run over the offset GROUPS (all dimensions but x), warps over rows; a lane
     // resolves the ksize[0] consecutive x of its group with one or two 32-byte slot lookups.
     if (xtable && fast) {
@@ -293,7 +458,8 @@ static int rulebook_build_impl(const int32_t* out_coords, int64_t n_out,
                                const insmos_slot_t* in_table, int64_t in_cap, const int32_t* parent,
                                const insmos_mapspec_t* spec, int32_t TM,
                                uint16_t* seg, uint32_t* entries, unsigned long long* pair_count, void* stream,
-                               const void* xtable = nullptr, int64_t xcap = 0, int32_t xstep = 0) {
+                               const void* xtable = nullptr, int64_t xcap = 0, int32_t xstep = 0,
+                               const void* lgrid = nullptr, int64_t lgcap = 0, const int32_t* lgstep = nullptr) {
     if (!out_coords || !spec || !seg || !entries || n_out < 0) return INSMOS_ERR_INVALID_ARG;
     if (parent) {
         if (spec->mode != 1) return INSMOS_ERR_INVALID_ARG;
@@ -318,14 +484,40 @@ static int rulebook_build_impl(const int32_t* out_coords, int64_t n_out,
     if (kprod != spec->K) return INSMOS_ERR_INVALID_ARG;
     if (n_out == 0) return INSMOS_OK;
     const size_t smem = sizeof(int) * (((size_t)TM * spec->K + 1) & ~(size_t)1) + sizeof(int64_t) * ((size_t)spec->K + TM) +
-                        sizeof(int) * ((size_t)spec->K * 4 + (size_t)TM * 5 + spec->K + 1);
+                        sizeof(int) * ((size_t)spec->K * 4 + (size_t)TM * 5 + spec->K + 1 + spec->K + (size_t)TM * 5);
+    LgGeom lg;
+    for (int d = 0; d < 4; ++d) { lg.step[d] = 1; lg.lsh[d] = 0; lg.mb[d] = 1; }
+    lg.ncand = 0;
+    const unsigned long long* lgkeys = nullptr;
+    const int32_t* lgrows = nullptr;
+    if (lgrid) {
+        if (lgcap <= 0 || (lgcap & (lgcap - 1)) || spec->mode != 0) return INSMOS_ERR_INVALID_ARG;
+        const int rc = lg_geometry(spec->ncol, lgstep, lg);
+        if (rc) return rc;
+        int ncand = 1;
+        for (int d = 0; d < spec->ndim; ++d) {
+            if (spec->q[d] != 1 || spec->e[d] != lg.step[d]) return INSMOS_ERR_UNSUPPORTED;      // digits must walk the input lattice
+            if (spec->ksize[d] > 60) return INSMOS_ERR_UNSUPPORTED;
+            // leaves a run of ksize indices can touch: 4-wide leaves in space (worst start = 3), 1-wide in time
+            lg.mb[d] = d < 3 ? ((spec->ksize[d] + 2) >> 2) + 1 : spec->ksize[d];
+            ncand *= lg.mb[d];
+            int sh = -1;                                               // the kernel reads lsh[] as log2(step) (or -1: divide)
+            for (int b = 0; b < 16; ++b) if (lg.step[d] == (1 << b)) sh = b;
+            lg.lsh[d] = sh;
+        }
+        if (ncand > 32) return INSMOS_ERR_UNSUPPORTED;
+        lg.ncand = ncand;
+        lgkeys = reinterpret_cast<const unsigned long long*>(lgrid);
+        lgrows = reinterpret_cast<const int32_t*>(lgkeys + lgcap);
+    }
     if (smem > 220 * 1024) return INSMOS_ERR_UNSUPPORTED;
     static thread_local insmos_smem_cfg_t configured;
     INSMOS_CHECK_CUDA(insmos_ensure_smem(k_rulebook_tiles, smem, configured));
     const int64_t n_tiles = ceil_div64(n_out, TM);
     k_rulebook_tiles<<<(unsigned)n_tiles, RB_THREADS, smem, (cudaStream_t)stream>>>(
         out_coords, n_out, in_table, (uint64_t)(in_cap - 1), *spec, TM, seg, entries, pair_count, parent,
-        reinterpret_cast<const XBlockSlot*>(xtable), (uint64_t)(xcap > 0 ? xcap - 1 : 0), xstep);
+        reinterpret_cast<const XBlockSlot*>(xtable), (uint64_t)(xcap > 0 ? xcap - 1 : 0), xstep,
+        lgkeys, lgrows, (uint64_t)(lgcap > 0 ? lgcap - 1 : 0), lg);
     INSMOS_CHECK_LAUNCH("k_rulebook_tiles");
     return INSMOS_OK;
 }
@@ -426,4 +618,17 @@ extern "C" int insmos_rulebook_build_xb(const int32_t* out_coords, int64_t n_out
     for (int d = 0; d < spec->ndim; ++d) if (spec->q[d] != 1) return INSMOS_ERR_UNSUPPORTED;
     return rulebook_build_impl(out_coords, n_out, in_table, in_cap, nullptr, spec, TM, seg, entries, pair_count, stream,
                                xtable, xcap, xstep);
+}
+
+// Same map as insmos_rulebook_build for an affine spec (mode 0, q = 1) whose kernel digits walk the input lattice
+// (e[d] == step[d]), probing the LEAF GRID of the input set (insmos_leafgrid_build).  Bit-identical output; the voxel table is
+// still needed for rows at the edge of the packable coordinate range.
+extern "C" int insmos_rulebook_build_lg(const int32_t* out_coords, int64_t n_out,
+                                        const insmos_slot_t* in_table, int64_t in_cap,
+                                        const void* grid, int64_t grid_cap, const int32_t* step,
+                                        const insmos_mapspec_t* spec, int32_t TM,
+                                        uint16_t* seg, uint32_t* entries, unsigned long long* pair_count, void* stream) {
+    if (!grid || !spec || !step) return INSMOS_ERR_INVALID_ARG;
+    return rulebook_build_impl(out_coords, n_out, in_table, in_cap, nullptr, spec, TM, seg, entries, pair_count, stream,
+                               nullptr, 0, 0, grid, grid_cap, step);
 }

@@ -349,8 +349,43 @@ def xblock_table(cs, xstep):
     return hit
 
 
-def build_rulebook(out_set, in_set, spec, TM=None, parent=None, xstep=None):
-    """tiled rule book of the map in_set -> out_set.  parent (int32 [n_out], optional): for a transposed map (mode-1
+USE_LEAFGRID = _os.environ.get("INSMOS_LEAFGRID", "1") != "0"
+# measured on B200 (C2 maps, profiles/r02_leafgrid_ab.txt): the grid pays for maps with >= 27 offsets over sets of >= ~50 k voxels
+# (3^4: 0.70 -> 0.33 ms at 496 k rows, 0.21 -> 0.13 at 226 k, 0.13 -> 0.08 at 94 k; 5^3: 0.41 -> 0.31); the 8-offset strided maps
+# and the small spconv sets are faster on plain voxel-table probes (one probe per pair, no grid to build).
+LEAFGRID_MIN_ROWS = int(_os.environ.get("INSMOS_LEAFGRID_MIN_ROWS", "50000"))
+LEAFGRID_MIN_K = int(_os.environ.get("INSMOS_LEAFGRID_MIN_K", "27"))
+
+
+def leafgrid(cs, step):
+    """leaf grid of a CoordSet whose coordinates are multiples of step[d] (cached on the set)."""
+    cache = cs.__dict__.setdefault("_leafgrid", {})
+    key = tuple(int(v) for v in step)
+    hit = cache.get(key)
+    if hit is None:
+        lib = _lib.load()
+        cap = lib.insmos_leafgrid_capacity(max(cs.n, 1))
+        grid = torch.empty(lib.insmos_leafgrid_bytes(cap), dtype=torch.uint8, device=cs.coords.device)
+        call("insmos_leafgrid_build", _p(cs.coords), cs.n, cs.ncol, _arr(C.c_int32, list(key)), _p(grid), cap, _stream())
+        hit = cache[key] = (grid, cap)
+    return hit
+
+
+def leafgrid_eligible(spec, step):
+    """affine map whose kernel digits walk the input lattice (e == step, q == 1) and whose neighbourhood spans <= 32 leaves"""
+    if spec.mode != 0 or step is None or len(step) != spec.ndim:
+        return False
+    ncand = 1
+    for d in range(spec.ndim):
+        if spec.q[d] != 1 or spec.e[d] != int(step[d]) or spec.ksize[d] > 60:
+            return False
+        ncand *= ((spec.ksize[d] + 2) >> 2) + 1 if d < 3 else spec.ksize[d]
+    return ncand <= 32
+
+
+def build_rulebook(out_set, in_set, spec, TM=None, parent=None, xstep=None, step=None):
+    """tiled rule book of the map in_set -> out_set.  step (optional): lattice step of in_set per dimension (tensor stride
+    of a MinkowskiEngine level, 1 for spconv indices): eligible maps then probe the set's leaf grid (leafgrid()).  parent (int32 [n_out], optional): for a transposed map (mode-1
     spec) the row of every output (fine) row's coarse cell in in_set, as returned by unique_coords(q): the map is then
     built without hash probes.  xstep (optional): tensor stride of in_set in x (its x coordinates are multiples of it):
     cube maps with >= 3 offsets in x then probe the set's x-block table."""
@@ -369,12 +404,20 @@ def build_rulebook(out_set, in_set, spec, TM=None, parent=None, xstep=None):
     use_xb = (USE_XBLOCK and parent is None and xstep is not None and spec.mode == 0 and spec.first_fastest == 1
               and spec.a[0] == 1 and spec.e[0] == int(xstep) and XBLOCK_MIN_KX <= spec.ksize[0] <= 8
               and all(spec.q[d] == 1 for d in range(spec.ndim)))
+    use_lg = (USE_LEAFGRID and parent is None and step is not None and leafgrid_eligible(spec, step)
+              and in_set.n >= LEAFGRID_MIN_ROWS and K >= LEAFGRID_MIN_K)
+    if use_lg:
+        use_xb = False
+        lgrid, lgcap = leafgrid(in_set, step)            # (its own C-ABI call: before the profile meta is armed)
     if use_xb:
         xt, xcap = xblock_table(in_set, int(xstep))      # (its own C-ABI call: before the profile meta is armed)
     prof = _lib.PROFILE is not None
     if prof:
         _lib.NEXT_META = {"n_out": n_out, "K": K, "ncol": out_set.ncol}
-    if use_xb:
+    if use_lg:
+        call("insmos_rulebook_build_lg", _p(out_set.coords), n_out, _p(in_set.table), in_set.cap, _p(lgrid), lgcap,
+             _arr(C.c_int32, [int(v) for v in step]), C.byref(spec), TM, _p(seg), _p(entries), _p(pc), _stream())
+    elif use_xb:
         call("insmos_rulebook_build_xb", _p(out_set.coords), n_out, _p(in_set.table), in_set.cap, _p(xt), xcap, int(xstep),
              C.byref(spec), TM, _p(seg), _p(entries), _p(pc), _stream())
     elif parent is not None:
