@@ -288,7 +288,15 @@ k_rulebook_tiles(const int32_t* __restrict__ out_coords, int64_t n_out,
         int cj[4];                                               // this lane's candidate leaf (j0..j3) -- a function of the lane only
         { int t = lane; for (int d = 0; d < 4; ++d) { cj[d] = t % lg.mb[d]; t /= lg.mb[d]; } }
         const int s1 = lg.mb[0], s2 = lg.mb[0] * lg.mb[1], s3 = lg.mb[0] * lg.mb[1] * lg.mb[2];
-        const int Kpad = (K + 31) & ~31;
+        // a lane owns the offsets k = lane, lane + 32, ... (<= LG_KI of them) for every row of its warp: their packed digits and
+        // bucket counts stay in registers (one shared-memory atomic per (warp, offset) at the end instead of one per pair),
+        // and the indexed loads of a row are all issued before the first is consumed
+        constexpr int LG_KI = 4;                                 // K <= 128
+        unsigned kp[LG_KI];
+        int cnt[LG_KI];
+#pragma unroll
+        for (int u = 0; u < LG_KI; ++u) { const int k = lane + 32 * u; kp[u] = k < K ? (unsigned)kpk[k] : 0u; cnt[u] = 0; }
+        const int nki = (K + 31) >> 5;
         for (int r = warp; r < TM; r += nwarps) {
             const bool row_ok = (row0 + r) < n_out;
             const int* c = tc + r * 5;
@@ -306,26 +314,36 @@ k_rulebook_tiles(const int32_t* __restrict__ out_coords, int64_t n_out,
                 continue;
             }
             const unsigned off = rowoff[r];
-            int myslot = -1;
+            int mybase = -1;                                         // first element of this lane's candidate leaf in lgrows, or -1
             if (off != 0xffffffffu && lane < lg.ncand) {
                 const int* b = rowblk + r * 4;
-                myslot = lg_find(lgkeys, lgmask, pack_key(c[0], b[0] + cj[0], b[1] + cj[1], b[2] + cj[2], b[3] + cj[3]));
+                const int slot = lg_find(lgkeys, lgmask, pack_key(c[0], b[0] + cj[0], b[1] + cj[1], b[2] + cj[2], b[3] + cj[3]));
+                mybase = slot >= 0 ? slot << 6 : -1;
             }
-            for (int k = lane; k < Kpad; k += 32) {                  // all lanes take part in the shuffle
-                const unsigned v = off + (unsigned)kpk[k < K ? k : 0];   // byte d = offset in the leaf + kernel digit (< 64)
-                const unsigned t0 = v & 0x00030303u;
-                const int loc = (int)((t0 | (t0 >> 6) | (t0 >> 12)) & 0x3fu);
-                const unsigned jj = v >> 2;
-                const int cand = (int)(jj & 0x3fu) + (int)((jj >> 8) & 0x3fu) * s1 + (int)((jj >> 16) & 0x3fu) * s2 + (int)(v >> 24) * s3;
-                const int slot = __shfl_sync(0xffffffffu, myslot, cand & 31);
-                if (k < K) {
-                    int res = -1;
-                    if (slot >= 0) res = __ldg(lgrows + (size_t)slot * 64 + loc);
-                    nbr[r * K + k] = res;
-                    if (res >= 0) atomicAdd(&hist[k], 1);
+            int res[LG_KI];
+#pragma unroll
+            for (int u = 0; u < LG_KI; ++u) {
+                res[u] = -1;
+                if (u < nki) {                                       // warp-uniform: all lanes take part in the shuffle
+                    const unsigned v = off + kp[u];                  // byte d = offset in the leaf + kernel digit (< 64)
+                    const unsigned t0 = v & 0x00030303u;
+                    const unsigned loc = (t0 | (t0 >> 6) | (t0 >> 12)) & 0x3fu;
+                    const unsigned jj = v >> 2;
+                    const int cand = (int)(jj & 0x3fu) + (int)((jj >> 8) & 0x3fu) * s1 + (int)((jj >> 16) & 0x3fu) * s2 + (int)(v >> 24) * s3;
+                    const int base = __shfl_sync(0xffffffffu, mybase, cand & 31);
+                    if (base >= 0 && lane + 32 * u < K) res[u] = __ldg(lgrows + (unsigned)(base + (int)loc));
                 }
             }
+#pragma unroll
+            for (int u = 0; u < LG_KI; ++u)
+                if (u < nki && lane + 32 * u < K) {
+                    nbr[r * K + lane + 32 * u] = res[u];
+                    cnt[u] += res[u] >= 0 ? 1 : 0;
+                }
         }
+#pragma unroll
+        for (int u = 0; u < LG_KI; ++u)
+            if (cnt[u] > 0) atomicAdd(&hist[lane + 32 * u], cnt[u]);
     } else
     // ---- phase A (x-block table): lanes run over the offset GROUPS (all dimensions but x), warps over rows; a lane
     // resolves the ksize[0] consecutive x of its group with one or two 32-byte slot lookups.
@@ -505,7 +523,7 @@ static int rulebook_build_impl(const int32_t* out_coords, int64_t n_out,
             for (int b = 0; b < 16; ++b) if (lg.step[d] == (1 << b)) sh = b;
             lg.lsh[d] = sh;
         }
-        if (ncand > 32) return INSMOS_ERR_UNSUPPORTED;
+        if (ncand > 32 || spec->K > 128) return INSMOS_ERR_UNSUPPORTED;
         lg.ncand = ncand;
         lgkeys = reinterpret_cast<const unsigned long long*>(lgrid);
         lgrows = reinterpret_cast<const int32_t*>(lgkeys + lgcap);

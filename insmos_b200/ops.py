@@ -380,7 +380,7 @@ def leafgrid_eligible(spec, step):
         if spec.q[d] != 1 or spec.e[d] != int(step[d]) or spec.ksize[d] > 60:
             return False
         ncand *= ((spec.ksize[d] + 2) >> 2) + 1 if d < 3 else spec.ksize[d]
-    return ncand <= 32
+    return ncand <= 32 and spec.K <= 128
 
 
 def build_rulebook(out_set, in_set, spec, TM=None, parent=None, xstep=None, step=None):
