@@ -25,8 +25,9 @@ for r in rd:
     d[name] = v
 
 FAMILY = [("k_spconv_tc", "insmos_sparse_conv_fwd_tc"), ("k_spconv_umma", "insmos_sparse_conv_fwd_umma"),
-          ("k_rulebook", "insmos_rulebook_build"), ("k_xblock", "insmos_rulebook_build"), ("k_spconv_cin1", "insmos_sparse_conv_fwd_ffma"),
-          ("k_spconv_ff", "insmos_sparse_conv_fwd_ffma"), ("k_linear", "insmos_linear_fwd"), ("k_nms", "insmos_nms_rotated"),
+          ("k_rulebook", "insmos_rulebook_build"), ("k_xblock", "insmos_rulebook_build"), ("k_leafgrid", "insmos_rulebook_build"),
+          ("k_spconv_cin1", "insmos_sparse_conv_fwd_ffma"), ("k_spconv_fma", "insmos_sparse_conv_fwd_fma"),
+          ("k_spconv_ff", "insmos_sparse_conv_fwd_ffma"), ("k_linear", "insmos_linear_fwd"), ("k_nms", "insmos_nms_rotated_pairs"),
           ("k_member", "insmos_box_membership"), ("k_conv_nhwc", "insmos_conv2d_nhwc_tcgen05")]
 def short(n):
     return re.sub(r"\(.*", "", n).replace("void ", "")
@@ -61,6 +62,16 @@ with open(out_prefix + "_summary.txt", "w") as fh:
             k[:44], b["n"], t, 100 * t / tot_us, (b["dram__bytes_read.sum"] + b["dram__bytes_write.sum"]) / 1e6, b["lts__t_bytes.sum"] / 1e6,
             b["smsp__issue_active.avg.pct_of_peak_sustained_active"] / t, b["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"] / t,
             b["sm__warps_active.avg.pct_of_peak_sustained_active"] / t, b["lts__t_sector_hit_rate.pct"] / t))
-json.dump({f: {"dram_bytes_per_forward": int(v["dram_bytes"]), "l2_bytes_per_forward": int(v["l2_bytes"]), "ncu_us": round(v["us"], 1),
-               "launches": int(v["launches"])} for f, v in fam.items()}, open(out_prefix + "_traffic.json", "w"), indent=1)
+import hashlib, os
+def _src_digest():
+    h = hashlib.sha256()
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "insmos_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+tj = {"_src_digest": _src_digest(), "_from": os.path.basename(out_prefix) + "_summary.txt (ncu over one forward of tools/one_forward.py)"}
+tj.update({f: {"dram_bytes_per_forward": int(v["dram_bytes"]), "l2_bytes_per_forward": int(v["l2_bytes"]), "ncu_us": round(v["us"], 1),
+               "launches": int(v["launches"])} for f, v in fam.items()})
+json.dump(tj, open(out_prefix + "_traffic.json", "w"), indent=1)
 print(open(out_prefix + "_summary.txt").read())
