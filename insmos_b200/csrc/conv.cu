@@ -247,54 +247,95 @@ static int launch_linear_g8(const float* in, const float* weight, float* out, in
 // One thread per row (ncu of k_linear_g8: 70-88 % issue-slot utilisation, two instructions per MAC -- an LDS per FFMA --
 // plus 3 shuffles per output): the row arrives as float4 loads, the weights are read as broadcast LDS.128 (every lane of
 // a warp reads the same address), COUTP accumulators stay in registers, no shuffles.  Cin % 4 == 0.
-template <int COUTP>
+// 1x1 convolution / Linear: thread t of a block owns the rows {t, t + 128, ...} -- R rows per thread, so that every weight
+// vector read from shared memory feeds R rows.  tools/micro/ffma_rate.cu: a broadcast LDS.128 costs four shared-memory
+// wavefronts, "2 LDS.128 + 8 FFMA" per lane tops out at 47 % of the FMA pipe; with R rows per thread the same loads feed
+// 8 R FFMAs.  The rows of a thread are 128 apart, so the lanes of a warp still read 32 consecutive rows (full sectors).
+// Outputs leave as float4, epilogue constants are read once per thread.
+template <int COUTP, int R>
 __global__ void __launch_bounds__(128)
 k_linear_row(const float* __restrict__ in, const float* __restrict__ W, float* __restrict__ out,
              int64_t n, int Cin, int Cout, insmos_epilogue_t ep) {
-    extern __shared__ __align__(16) float sw[];                   // [Cin][COUTP]
+    extern __shared__ __align__(16) float sw[];                   // [Cin][COUTP] | scale[COUTP] | shift[COUTP] | bias[COUTP]
+    float* sc = sw + (size_t)Cin * COUTP;
     for (int i = threadIdx.x; i < Cin * COUTP; i += blockDim.x) {
         const int ci = i / COUTP, co = i - ci * COUTP;
         sw[i] = co < Cout ? W[ci * Cout + co] : 0.0f;
     }
+    for (int c = threadIdx.x; c < COUTP; c += blockDim.x) {
+        sc[c] = (ep.scale && c < Cout) ? ep.scale[c] : 1.0f;
+        sc[COUTP + c] = (ep.scale && c < Cout) ? ep.shift[c] : 0.0f;
+        sc[2 * COUTP + c] = (ep.bias && c < Cout) ? ep.bias[c] : 0.0f;
+    }
     __syncthreads();
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n) return;
-    const float4* x = reinterpret_cast<const float4*>(in + row * Cin);
-    float acc[COUTP];
+    const int64_t row0 = (int64_t)blockIdx.x * (128 * R) + threadIdx.x;
+    const float4* x[R];
+    bool ok[R];
 #pragma unroll
-    for (int c = 0; c < COUTP; ++c) acc[c] = 0.0f;
-    for (int c4 = 0; c4 < Cin / 4; c4 += 2) {                      // two float4 in flight
-        const float4 v0 = __ldg(x + c4);
-        const float4 v1 = (c4 + 1 < Cin / 4) ? __ldg(x + c4 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    for (int r = 0; r < R; ++r) {
+        ok[r] = row0 + 128 * r < n;
+        x[r] = reinterpret_cast<const float4*>(in + (ok[r] ? row0 + 128 * r : 0) * Cin);
+    }
+    float acc[R][COUTP];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int ci = c4 * 4 + u;
-            if (ci < Cin) {
-                const float4* w = reinterpret_cast<const float4*>(sw + ci * COUTP);
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-                for (int q = 0; q < COUTP / 4; ++q) {
-                    const float4 ww = w[q];
-                    acc[4 * q + 0] = __fmaf_rn(vv[u], ww.x, acc[4 * q + 0]);
-                    acc[4 * q + 1] = __fmaf_rn(vv[u], ww.y, acc[4 * q + 1]);
-                    acc[4 * q + 2] = __fmaf_rn(vv[u], ww.z, acc[4 * q + 2]);
-                    acc[4 * q + 3] = __fmaf_rn(vv[u], ww.w, acc[4 * q + 3]);
+        for (int c = 0; c < COUTP; ++c) acc[r][c] = 0.0f;
+    for (int c4 = 0; c4 < Cin / 4; ++c4) {
+        float4 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = ok[r] ? __ldg(x[r] + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float4* w = reinterpret_cast<const float4*>(sw + (c4 * 4 + u) * COUTP);
+#pragma unroll
+            for (int q = 0; q < COUTP / 4; ++q) {
+                const float4 ww = w[q];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float xv = u == 0 ? v[r].x : u == 1 ? v[r].y : u == 2 ? v[r].z : v[r].w;
+                    acc[r][4 * q + 0] = __fmaf_rn(xv, ww.x, acc[r][4 * q + 0]);
+                    acc[r][4 * q + 1] = __fmaf_rn(xv, ww.y, acc[r][4 * q + 1]);
+                    acc[r][4 * q + 2] = __fmaf_rn(xv, ww.z, acc[r][4 * q + 2]);
+                    acc[r][4 * q + 3] = __fmaf_rn(xv, ww.w, acc[r][4 * q + 3]);
                 }
             }
         }
     }
+    const bool vec = (Cout & 3) == 0;
 #pragma unroll
-    for (int c = 0; c < COUTP; ++c)
-        if (c < Cout) out[row * Cout + c] = apply_epilogue(acc[c], c, row, Cout, ep);
+    for (int r = 0; r < R; ++r) {
+        if (!ok[r]) continue;
+        const int64_t row = row0 + 128 * r;
+#pragma unroll
+        for (int c = 0; c < COUTP; ++c) {
+            float t = acc[r][c];
+            if (ep.scale) t = __fmaf_rn(t, sc[c], sc[COUTP + c]);
+            if (ep.bias) t += sc[2 * COUTP + c];
+            if (ep.residual && c < Cout) t += __ldg(ep.residual + row * Cout + c);
+            if (ep.relu) t = fmaxf(t, 0.0f);
+            acc[r][c] = t;
+        }
+        if (vec) {
+#pragma unroll
+            for (int q = 0; q < COUTP / 4; ++q)
+                if (4 * q < Cout)
+                    *reinterpret_cast<float4*>(out + row * Cout + 4 * q) = make_float4(acc[r][4 * q], acc[r][4 * q + 1], acc[r][4 * q + 2], acc[r][4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < COUTP; ++c)
+                if (c < Cout) out[row * Cout + c] = acc[r][c];
+        }
+    }
 }
 
-template <int COUTP>
+template <int COUTP, int R>
 static int launch_linear_row(const float* in, const float* weight, float* out, int64_t n, int Cin, int Cout,
                              const insmos_epilogue_t& ep, cudaStream_t st) {
-    const size_t smem = sizeof(float) * (size_t)Cin * COUTP;
+    const size_t smem = sizeof(float) * ((size_t)Cin * COUTP + 3 * COUTP);
     static thread_local insmos_smem_cfg_t configured;
-    INSMOS_CHECK_CUDA(insmos_ensure_smem(k_linear_row<COUTP>, smem, configured));
-    k_linear_row<COUTP><<<(unsigned)ceil_div64(n, 128), 128, smem, st>>>(in, weight, out, n, Cin, Cout, ep);
+    INSMOS_CHECK_CUDA(insmos_ensure_smem(k_linear_row<COUTP, R>, smem, configured));
+    k_linear_row<COUTP, R><<<(unsigned)ceil_div64(n, 128 * R), 128, smem, st>>>(in, weight, out, n, Cin, Cout, ep);
     INSMOS_CHECK_LAUNCH("k_linear_row");
     return INSMOS_OK;
 }
@@ -308,10 +349,15 @@ extern "C" int insmos_linear_fwd(const float* in, int64_t n, int32_t Cin, const 
     if (n == 0) return INSMOS_OK;
     if (Cout <= 32 && (Cin & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (size_t)Cin * 32 * sizeof(float) <= 64 * 1024 &&
         getenv("INSMOS_LINEAR_G8") == nullptr) {
-        if (Cout <= 4) return launch_linear_row<4>(in, weight, out, n, Cin, Cout, ep, (cudaStream_t)stream);
-        if (Cout <= 8) return launch_linear_row<8>(in, weight, out, n, Cin, Cout, ep, (cudaStream_t)stream);
-        if (Cout <= 16) return launch_linear_row<16>(in, weight, out, n, Cin, Cout, ep, (cudaStream_t)stream);
-        return launch_linear_row<32>(in, weight, out, n, Cin, Cout, ep, (cudaStream_t)stream);
+        // rows per thread: as many as the accumulators allow while the grid still covers the SMs a few times
+        const bool small = n < 148ll * 128 * 8;
+        if (Cout <= 4) return small ? launch_linear_row<4, 2>(in, weight, out, n, Cin, Cout, ep, (cudaStream_t)stream)
+                                    : launch_linear_row<4, 4>(in, weight, out, n, Cin, Cout, ep, (cudaStream_t)stream);
+        if (Cout <= 8) return small ? launch_linear_row<8, 2>(in, weight, out, n, Cin, Cout, ep, (cudaStream_t)stream)
+                                    : launch_linear_row<8, 4>(in, weight, out, n, Cin, Cout, ep, (cudaStream_t)stream);
+        if (Cout <= 16) return small ? launch_linear_row<16, 2>(in, weight, out, n, Cin, Cout, ep, (cudaStream_t)stream)
+                                     : launch_linear_row<16, 4>(in, weight, out, n, Cin, Cout, ep, (cudaStream_t)stream);
+        return launch_linear_row<32, 2>(in, weight, out, n, Cin, Cout, ep, (cudaStream_t)stream);
     }
     if (Cout <= 32 && (size_t)Cin * 33 * sizeof(float) <= 160 * 1024) {
         if (Cout <= 8) return launch_linear_g8<8>(in, weight, out, n, Cin, Cout, ep, (cudaStream_t)stream);
