@@ -390,6 +390,52 @@ int insmos_instance_stats(const int32_t* ids, int32_t ncls, int32_t col, int64_t
 int insmos_relabel_instances(const int32_t* ids, int32_t ncls, int32_t col, int64_t n, const int32_t* new_label,
                              int32_t nb, int32_t* labels, void* stream);
 
+/* ---- training step (BASELINE config 5) -----------------------------------------------
+ * The reference trains through autograd over MinkowskiEngine / spconv (models/models.py:61-98,330-347,
+ * scripts/train.py:74-79).  The DATA gradient of a sparse convolution is insmos_sparse_conv_fwd_* over the transposed rule
+ * book with transposed weights; the entry points below are the pieces that have no forward counterpart. */
+
+/* number of tile slices (partial matrices) insmos_sparse_conv_wgrad needs for this map: partial holds S*K*Cin*Cout floats */
+int32_t insmos_sparse_conv_wgrad_slices(int64_t n_out, int32_t TM, int32_t K, int32_t Cin);
+
+/* WEIGHT gradient of MinkowskiConvolution / SubMConv3d / SparseConv3d / SparseInverseConv3d (replaces the autograd backward of
+ * ME's ConvolutionFunction / spconv's SparseConvFunction at the call sites minkunet.py:139-181, spconv_unet.py:284-406):
+ * dweight[k][ci][co] = sum over the pairs (i,o) of bucket k of in[i][ci] * dout[o][co].  Deterministic (fixed summation
+ * order: per-slice partial matrices added in slice order).  [dev] in [n_in,Cin], dout [n_out,Cout], seg/entries = the
+ * forward rule book, partial [S,K,Cin,Cout] scratch, dweight [K,Cin,Cout]. */
+int insmos_sparse_conv_wgrad(const float* in, int64_t n_in, int32_t Cin, const float* dout, int64_t n_out, int32_t Cout,
+                             const uint16_t* seg, const uint32_t* entries, int32_t TM, int32_t K,
+                             float* partial, int32_t S, float* dweight, void* stream);
+
+/* column reductions over [n,C] fp32 matrices into fp64 sums (train-mode MinkowskiBatchNorm / nn.BatchNorm1d,
+ * minkunet.py:52-131, spconv_unet.py:118):  mode 0: out0 = sum a;  mode 1: out0 = sum (a - mean)^2;
+ * mode 2: g = (gate == NULL || gate > 0) ? a : 0, out0 = sum g, out1 = sum g * (b - mean) * invstd.   C <= 1024. */
+int insmos_column_moments(const float* a, const float* b, const float* gate, const float* mean, const float* invstd,
+                          int64_t n, int32_t C, int32_t mode, double* out0, double* out1, void* stream);
+
+/* BatchNorm backward, elementwise part: dx = coef * (g - m0 - xhat * m1), g = dy gated by gate > 0 (fused ReLU) */
+int insmos_bn_bwd_apply(const float* dy, const float* x, const float* gate, const float* mean, const float* invstd,
+                        const float* coef, const float* m0, const float* m1, int64_t n, int32_t C, float* dx, void* stream);
+
+/* out[idx[i],0:C] += src[i,0:C] (idx < 0 skipped; src row stride ldsrc): backward of insmos_gather_rows /
+ * insmos_build_current_points / gather_features_by_pc_voxel_id.  out must be initialised by the caller. */
+int insmos_scatter_add_rows(const float* src, int32_t C, int32_t ldsrc, const int32_t* idx, int64_t n, float* out, void* stream);
+
+/* CenterHead.get_targets_single (models/backbones_2d/center_head.py:171-249) for one sample, one block per box instead of
+ * the reference's Python loop: gt_boxes [n_box,8] (x,y,z,dx,dy,dz,yaw,class 1..ncls) -> heatmap [ncls,H,W] (Gaussian
+ * peaks, running maximum), anno_boxes [max_objs,8], inds int64 [max_objs], masks uint8 [max_objs] (all zeroed first).
+ * range_is_fp64: 0 when the configured point-cloud range is integral (torch then keeps the centre arithmetic in fp32), 1 when
+ * it holds floats (fp32 box - fp64 range promotes to fp64). */
+int insmos_center_targets(const float* gt_boxes, int32_t n_box, int32_t max_objs, int32_t H, int32_t W, int32_t ncls,
+                          double x_min, double y_min, int32_t range_is_fp64, float vx, float vy, int32_t out_size_factor,
+                          float min_overlap, int32_t min_radius, float* heatmap, float* anno_boxes, int64_t* inds,
+                          uint8_t* masks, void* stream);
+
+/* torch.optim.Adam step (models/models.py:185-190) over one flat fp32 parameter buffer; grad_scale multiplies the gradient
+ * first (1/world_size after the data-parallel all-reduce); step counts from 1. */
+int insmos_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int64_t step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

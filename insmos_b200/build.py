@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libinsmos_b200.so")
-SOURCES = ["coords.cu", "rulebook.cu", "conv.cu", "conv_tc.cu", "conv_ffma.cu", "conv_fma.cu", "detect.cu", "bev.cu", "bev_tcgen05.cu", "spconv_umma.cu", "staging.cu", "refine.cu"]
+SOURCES = ["coords.cu", "rulebook.cu", "conv.cu", "conv_tc.cu", "conv_ffma.cu", "conv_fma.cu", "detect.cu", "bev.cu", "bev_tcgen05.cu", "spconv_umma.cu", "staging.cu", "refine.cu", "train.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -16,6 +16,7 @@ import math
 import torch
 import torch.nn as nn
 
+from insmos_b200 import autograd as _ag
 from insmos_b200 import ops
 
 from . import utils  # noqa: F401  (ME.utils.sparse_collate, kaiming_normal_, batched_coordinates)
@@ -119,8 +120,8 @@ class SparseTensor:
 
     def slice(self, field):
         """features of the voxel every point of `field` fell into (motionnet.py:38)."""
-        return TensorField(ops.gather_rows(self._F, field.inverse_mapping), coordinates=field._coords.clone(),
-                           _skip_check=True)
+        gather = _ag.gather_rows if _ag.needs_grad(self._F) else ops.gather_rows
+        return TensorField(gather(self._F, field.inverse_mapping), coordinates=field._coords.clone(), _skip_check=True)
 
 
 class TensorField:
@@ -163,7 +164,7 @@ def cat(*tensors):
     f = out.F
     for t in tensors[1:]:
         assert t.coordinate_map_key == out.coordinate_map_key, "ME.cat: tensors must share a coordinate map"
-        f = ops.concat2(f, t.F)
+        f = torch.cat([f, t.F], 1) if _ag.needs_grad(f, t.F) else ops.concat2(f, t.F)
     return out._like(f)
 
 
@@ -187,11 +188,12 @@ class MinkowskiBatchNorm(nn.Module):
             self._folded = (ver, scale.contiguous(), shift.contiguous())
         return self._folded[1], self._folded[2]
 
-    def forward(self, x):
+    def forward(self, x, relu=False):
         if self.training or not self.bn.track_running_stats:
-            return x._like(self.bn(x.F))            # training statistics: torch (training loop is out of scope)
+            # batch statistics (training step): column-moment kernels + fused normalise(+ReLU), with autograd
+            return x._like(_ag.batch_norm_train(self.bn, x.F, relu=relu))
         s, t = self.folded()
-        return x._like(ops.affine_act(x.F, scale=s, shift=t))
+        return x._like(ops.affine_act(x.F, scale=s, shift=t, relu=relu))
 
 
 class MinkowskiReLU(nn.Module):
@@ -201,6 +203,8 @@ class MinkowskiReLU(nn.Module):
 
     def forward(self, x):
         f = x.F
+        if _ag.needs_grad(f):
+            return x._like(torch.relu(f))
         return x._like(ops.affine_act(f, relu=True, out=f if self.inplace and not f.requires_grad else None))
 
 
@@ -240,7 +244,37 @@ class _ConvBase(nn.Module):
             if self.bias is not None:
                 self.bias.uniform_(-stdv, stdv)
 
+    def _forward_train(self, x):
+        """differentiable path (autograd.sparse_conv): forward kernel, dgrad = forward kernel over the transposed map, wgrad kernel"""
+        mgr, in_key = x.coordinate_manager, x.coordinate_map_key
+        if self.kernel_volume == 1 and all(s == 1 for s in self.stride):
+            return x._like(_ag.linear(x.F, self.kernel, self.bias))
+        w = self.kernel if self.kernel.dim() == 3 else self.kernel.view(1, *self.kernel.shape)
+        if not self.transposed:
+            if all(s == 1 for s in self.stride):
+                if any(k % 2 == 0 for k in self.kernel_size):
+                    raise NotImplementedError("training through a stride-1 convolution with an even kernel")
+                out_key = in_key
+                rb = mgr.rulebook("conv", in_key, out_key, self.kernel_size, self.stride)
+                rb_t, flip = rb, True                                      # own transpose with mirrored offsets
+            else:
+                out_key = mgr.stride(in_key, self.stride)
+                rb = mgr.rulebook("conv", in_key, out_key, self.kernel_size, self.stride)
+                ks, st = self.kernel_size, self.stride
+                rb_t, flip = (lambda: mgr.rulebook("up", out_key, in_key, ks, st)), False
+        else:
+            out_key = tuple(k // s for k, s in zip(in_key, self.stride))
+            if out_key not in mgr.sets or self.kernel_size != self.stride:
+                raise NotImplementedError("transposed convolution off the InsMOS path")
+            rb = mgr.rulebook("up", in_key, out_key, self.kernel_size, self.stride)
+            ks, st = self.kernel_size, self.stride
+            rb_t, flip = (lambda: mgr.rulebook("conv", out_key, in_key, ks, st)), False
+        f = _ag.sparse_conv(x.F, w, rb, rb_t, flip)
+        return x._like(f if self.bias is None else f + self.bias, out_key)
+
     def forward(self, x, bn=None, relu=False, residual=None, algo=0):
+        if bn is None and not relu and residual is None and _ag.needs_grad(x.F, self.kernel, self.bias):
+            return self._forward_train(x)
         scale, shift = _fold(bn)
         bias = None if self.bias is None else self.bias.view(-1)
         mgr, in_key = x.coordinate_manager, x.coordinate_map_key

@@ -26,7 +26,7 @@ class BasicBlock(nn.Module):
 
     def forward(self, x):
         if self.training:
-            out = self.relu(self.norm1(self.conv1(x)))
+            out = self.norm1(self.conv1(x), relu=True)
             out = self.norm2(self.conv2(out))
             res = x if self.downsample is None else self.downsample(x)
             return self.relu(out._like(out.F + res.F))

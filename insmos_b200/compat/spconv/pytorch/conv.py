@@ -3,6 +3,7 @@ import math
 import torch
 import torch.nn as nn
 
+from insmos_b200 import autograd as _ag
 from insmos_b200 import ops
 
 from .core import IndiceData, SparseConvTensor
@@ -114,6 +115,24 @@ class SparseConvolution(SparseModule):
         cin = x.features.shape[1]
         if cin < self.in_channels:
             raise ValueError("SparseConvolution: %d input channels, layer expects %d" % (cin, self.in_channels))
+        if bn is None and not relu and residual is None and _ag.needs_grad(x.features, self.weight, self.bias):
+            # training step: differentiable kernel-major weight, transposed map by kind
+            wk = self.weight.reshape(self.out_channels, -1, self.in_channels).permute(1, 2, 0)
+            if cin > self.in_channels:
+                wk = torch.cat([wk, wk.new_zeros((wk.shape[0], cin - self.in_channels, wk.shape[2]))], 1)
+            if self.inverse:
+                rb_t, flip = data.forward_rulebook, False
+            elif self.subm:
+                if any(k % 2 == 0 for k in self.kernel_size):
+                    raise NotImplementedError("training through a submanifold convolution with an even kernel")
+                rb_t, flip = rb, True
+            else:
+                rb_t, flip = data.inverse_rulebook, False
+            f = _ag.sparse_conv(x.features, wk.contiguous(), rb, rb_t, flip, getattr(x, "grad_cols", None))
+            if self.bias is not None:
+                f = f + self.bias
+            return SparseConvTensor(f, out_set.coords, out_shape, x.batch_size, indice_dict=x.indice_dict,
+                                    benchmark=x.benchmark, coordset=out_set)
         f = ops.sparse_conv(x.features, self.kernel_major_weight(cin), rb, scale=scale, shift=shift, bias=self.bias,
                             residual=residual, relu=relu, algo=algo)
         return SparseConvTensor(f, out_set.coords, out_shape, x.batch_size, indice_dict=x.indice_dict,

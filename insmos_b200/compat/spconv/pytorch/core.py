@@ -61,6 +61,13 @@ class SparseConvTensor:
         if self.batch_size != 1:
             raise NotImplementedError("dense(): batch_size 1 on the InsMOS path (spconv_unet.py:282)")
         D, H, W = self.spatial_shape
+        if torch.is_grad_enabled() and self.features.requires_grad:
+            # training: index_put keeps the graph (the scatter kernel has no backward; this is plumbing, one call per step)
+            ind = self.indices.long()
+            out = self.features.new_zeros((self.features.shape[1], D, H, W))
+            out[:, ind[:, 1], ind[:, 2], ind[:, 3]] = self.features.t()
+            out = out.unsqueeze(0)
+            return out if channels_first else out.permute(0, 2, 3, 4, 1).contiguous()
         out = ops.dense_scatter(self.features, self.indices.to(torch.int32).contiguous(), D, H, W).unsqueeze(0)
         return out if channels_first else out.permute(0, 2, 3, 4, 1).contiguous()
 

@@ -47,6 +47,13 @@ class SparseSequential(SparseModule):
                 x = m(x, bn=mods[i + 1], relu=relu)
                 i += 3 if relu else 2
                 continue
+            if self.training and isinstance(m, nn.BatchNorm1d) and isinstance(x, SparseConvTensor) and x.features.shape[0] != 0:
+                # batch statistics on the library's column-moment kernels, ReLU fused when it follows (training step, N3)
+                from insmos_b200 import autograd as _ag
+                relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+                x = x.replace_feature(_ag.batch_norm_train(m, x.features, relu=relu))
+                i += 2 if relu else 1
+                continue
             if _is_sparse(m):
                 x = m(x)
             elif isinstance(x, SparseConvTensor):

@@ -33,4 +33,6 @@ class PointToVoxel:
 def gather_features_by_pc_voxel_id(seg_res_features, pc_voxel_id, invalid_value=0):
     if invalid_value != 0:
         raise NotImplementedError
-    return ops.gather_rows(seg_res_features.contiguous(), pc_voxel_id.to(torch.int32).contiguous())
+    from insmos_b200 import autograd as _ag
+    gather = _ag.gather_rows if _ag.needs_grad(seg_res_features) else ops.gather_rows
+    return gather(seg_res_features.contiguous(), pc_voxel_id.to(torch.int32).contiguous())

@@ -1,0 +1,369 @@
+// Training-side kernels (BASELINE config 5): weight gradient of the sparse convolution over the
+// tiled rule book, column moments / backward reductions of train-mode BatchNorm, scatter-add (backward of the row gathers),
+// CenterHead target assignment (center_head.py:126-249) and a fused Adam step over a flat parameter buffer.
+// The DATA gradient of a sparse convolution needs no kernel of its own: it is the forward kernel run over the transposed
+// rule book with transposed weights (insmos_b200/autograd.py).
+#include "common.cuh"
+#include <math.h>
+
+// ------------------------------------------------------------------------------------------------
+// wgrad:  dW[k][ci][co] = sum over the pairs (i, o) of bucket k of  x[i][ci] * dy[o][co]
+//
+// grid = (K, S, ceil(Cin / CIB)); a block owns offset k, the tiles t = s, s + S, ... of slice s and CIB input channels.
+// Warp w of the block walks the tiles  s + S * (w + 8 j): the pairs of bucket (tile, k) are taken G at a time
+// (G = 32 / CoutP lane groups, lane = (g, co)); a lane keeps acc[CIB][M] for its output channels co + 32 m: per pair one
+// coalesced load of the dy row, CIB / 4 broadcast float4 loads of the x row, CIB * M FFMAs.  The lane groups are then
+// summed by shuffles, the warps through shared memory (fixed order), and the block writes ITS partial matrix
+// partial[s][k][ci][co]; k_wgrad_reduce adds the S partials in slice order -- no atomics, the result does not depend on
+// scheduling.
+#define WG_CIB 16
+#define WG_WARPS 8
+template <int M>
+__global__ void __launch_bounds__(WG_WARPS * 32)
+k_spconv_wgrad(const float* __restrict__ x, const float* __restrict__ dy, const uint16_t* __restrict__ seg,
+               const uint32_t* __restrict__ entries, int TM, int K, int Cin, int Cout, int CoutP, int64_t n_tiles, int S,
+               float* __restrict__ partial) {
+    __shared__ float red[WG_WARPS][WG_CIB][33];
+    const int k = blockIdx.x, s = blockIdx.y, ci0 = blockIdx.z * WG_CIB;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int G = 32 / CoutP, g = lane / CoutP, c0 = lane - g * CoutP;
+    float acc[WG_CIB][M];
+#pragma unroll
+    for (int a = 0; a < WG_CIB; ++a)
+#pragma unroll
+        for (int m = 0; m < M; ++m) acc[a][m] = 0.0f;
+    const bool vec = (Cin & 3) == 0;                                   // rows of x are 16-byte aligned multiples
+    for (int64_t tile = s + (int64_t)S * warp; tile < n_tiles; tile += (int64_t)S * WG_WARPS) {
+        const uint16_t* tseg = seg + tile * (K + 1);
+        const int start = tseg[k], n = (int)tseg[k + 1] - start;
+        const uint32_t* tent = entries + tile * (int64_t)TM * K + start;
+        for (int p0 = 0; p0 < n; p0 += G) {
+            const int p = p0 + g;
+            if (p >= n) continue;
+            const uint32_t e = __ldg(tent + p);
+            const int64_t i = e & INSMOS_ROW_MASK, o = tile * TM + (e >> INSMOS_ROW_BITS);
+            float d[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) { const int co = c0 + 32 * m; d[m] = co < Cout ? __ldg(dy + o * Cout + co) : 0.0f; }
+            const float* xr = x + i * Cin + ci0;
+            float xv[WG_CIB];
+            if (vec && ci0 + WG_CIB <= Cin) {
+#pragma unroll
+                for (int q = 0; q < WG_CIB / 4; ++q) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(xr) + q);
+                    xv[4 * q] = v.x; xv[4 * q + 1] = v.y; xv[4 * q + 2] = v.z; xv[4 * q + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < WG_CIB; ++a) xv[a] = ci0 + a < Cin ? __ldg(xr + a) : 0.0f;
+            }
+#pragma unroll
+            for (int a = 0; a < WG_CIB; ++a)
+#pragma unroll
+                for (int m = 0; m < M; ++m) acc[a][m] = __fmaf_rn(xv[a], d[m], acc[a][m]);
+        }
+    }
+    // lane groups -> group 0 (fixed shuffle tree), then per 32-channel slab m: warps -> shared memory -> fixed-order sum
+    float* dst = partial + (((size_t)s * K + k) * Cin) * Cout;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+#pragma unroll
+        for (int a = 0; a < WG_CIB; ++a) {
+            float v = acc[a][m];
+            for (int off = 16; off >= CoutP; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            if (g == 0) red[warp][a][c0] = v;
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < WG_CIB * 32; idx += blockDim.x) {
+            const int a = idx >> 5, c = idx & 31, co = c + 32 * m;
+            if (ci0 + a >= Cin || co >= Cout || c >= CoutP) continue;
+            float v = 0.0f;
+#pragma unroll
+            for (int w = 0; w < WG_WARPS; ++w) v += red[w][a][c];
+            dst[(size_t)(ci0 + a) * Cout + co] = v;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_wgrad_reduce(const float* __restrict__ partial, int S, int64_t n, float* __restrict__ dw) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = 0.0f;
+    for (int s = 0; s < S; ++s) v += partial[(size_t)s * n + i];
+    dw[i] = v;
+}
+
+extern "C" int32_t insmos_sparse_conv_wgrad_slices(int64_t n_out, int32_t TM, int32_t K, int32_t Cin) {
+    const int64_t n_tiles = ceil_div64(n_out > 0 ? n_out : 1, TM);
+    const int nz = (Cin + WG_CIB - 1) / WG_CIB;
+    int64_t S = ceil_div64(1184, (int64_t)K * nz);                     // ~8 blocks per SM
+    if (S > 64) S = 64;
+    if (S > n_tiles) S = n_tiles;
+    if (S < 1) S = 1;
+    return (int32_t)S;
+}
+
+extern "C" int insmos_sparse_conv_wgrad(const float* in, int64_t n_in, int32_t Cin, const float* dout, int64_t n_out,
+                                        int32_t Cout, const uint16_t* seg, const uint32_t* entries, int32_t TM, int32_t K,
+                                        float* partial, int32_t S, float* dweight, void* stream) {
+    if (!dweight || !partial || !seg || !entries || Cin <= 0 || Cout <= 0 || K <= 0 || TM <= 0 || n_in < 0 || n_out < 0 ||
+        (n_in > 0 && !in) || (n_out > 0 && !dout))
+        return INSMOS_ERR_INVALID_ARG;
+    if (S != insmos_sparse_conv_wgrad_slices(n_out, TM, K, Cin)) return INSMOS_ERR_INVALID_ARG;
+    if (Cout > 128 || K > 65535) return INSMOS_ERR_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = (int64_t)K * Cin * Cout;
+    if (n_out == 0 || n_in == 0) {
+        INSMOS_CHECK_CUDA(cudaMemsetAsync(dweight, 0, sizeof(float) * n, st));
+        return INSMOS_OK;
+    }
+    int CoutP = 1;
+    while (CoutP < Cout && CoutP < 32) CoutP <<= 1;
+    const int M = (Cout + 31) / 32;
+    const int64_t n_tiles = ceil_div64(n_out, TM);
+    const dim3 grid((unsigned)K, (unsigned)S, (unsigned)((Cin + WG_CIB - 1) / WG_CIB));
+    switch (M) {
+        case 1: k_spconv_wgrad<1><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, CoutP, n_tiles, S, partial); break;
+        case 2: k_spconv_wgrad<2><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, CoutP, n_tiles, S, partial); break;
+        case 3: k_spconv_wgrad<3><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, CoutP, n_tiles, S, partial); break;
+        default: k_spconv_wgrad<4><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, CoutP, n_tiles, S, partial); break;
+    }
+    INSMOS_CHECK_LAUNCH("k_spconv_wgrad");
+    k_wgrad_reduce<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(partial, S, n, dweight);
+    INSMOS_CHECK_LAUNCH("k_wgrad_reduce");
+    return INSMOS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Column reductions over x [n, C] (C <= 1024), the building block of train-mode BatchNorm (forward: mean, then the centred
+// second moment -- two passes, the variance is never formed as E[x^2] - E[x]^2; backward: sum(dy) and sum(dy * xhat)).
+//   mode 0: out0[c] = sum_r a[r][c]
+//   mode 1: out0[c] = sum_r (a[r][c] - mean[c])^2
+//   mode 2: g = gate ? (gate[r][c] > 0 ? a : 0) : a;  out0[c] = sum_r g,  out1[c] = sum_r g * (b[r][c] - mean[c]) * invstd[c]
+// Block partials are accumulated in double; a block adds its column sums to the double outputs with atomicAdd (the order
+// of the ~600 block contributions varies, in double that is invisible after rounding to fp32).
+#define CM_THREADS 256
+__global__ void __launch_bounds__(CM_THREADS)
+k_column_moments(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gate,
+                 const float* __restrict__ mean, const float* __restrict__ invstd, int64_t n, int C, int mode,
+                 int rows_per_block, double* __restrict__ out0, double* __restrict__ out1) {
+    extern __shared__ double sh[];                                      // [2][RL][C]
+    const int RL = CM_THREADS / C > 0 ? CM_THREADS / C : 1;             // row lanes (C <= 256), else columns are looped
+    const int CS = C <= CM_THREADS ? C : CM_THREADS;                    // column stride of the shared partials
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = (r0 + rows_per_block < n) ? r0 + rows_per_block : n;
+    for (int cbase = 0; cbase < C; cbase += CM_THREADS) {
+        const int c = cbase + (C <= CM_THREADS ? threadIdx.x % C : threadIdx.x);
+        const int rl = C <= CM_THREADS ? threadIdx.x / C : 0;
+        double s0 = 0.0, s1 = 0.0;
+        if (c < C && rl < RL) {
+            const float mu = (mode != 0) ? mean[c] : 0.0f;
+            const float is = (mode == 2) ? invstd[c] : 0.0f;
+            for (int64_t r = r0 + rl; r < r1; r += RL) {
+                const float v = a[r * C + c];
+                if (mode == 0) s0 += (double)v;
+                else if (mode == 1) { const float d = v - mu; s0 += (double)d * (double)d; }
+                else {
+                    const float gv = (gate && !(gate[r * C + c] > 0.0f)) ? 0.0f : v;
+                    s0 += (double)gv;
+                    s1 += (double)gv * (double)((b[r * C + c] - mu) * is);
+                }
+            }
+        }
+        if (c < C && rl < RL) { sh[rl * CS + (c - cbase)] = s0; sh[(RL + rl) * CS + (c - cbase)] = s1; }
+        __syncthreads();
+        if (rl == 0 && c < C) {
+            double t0 = 0.0, t1 = 0.0;
+            for (int q = 0; q < RL; ++q) { t0 += sh[q * CS + (c - cbase)]; t1 += sh[(RL + q) * CS + (c - cbase)]; }
+            atomicAdd(out0 + c, t0);
+            if (mode == 2) atomicAdd(out1 + c, t1);
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int insmos_column_moments(const float* a, const float* b, const float* gate, const float* mean, const float* invstd,
+                                     int64_t n, int32_t C, int32_t mode, double* out0, double* out1, void* stream) {
+    if (!out0 || C <= 0 || C > 1024 || n < 0 || mode < 0 || mode > 2 || (n > 0 && !a) || (mode != 0 && !mean) ||
+        (mode == 2 && (!b || !invstd || !out1)))
+        return INSMOS_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    INSMOS_CHECK_CUDA(cudaMemsetAsync(out0, 0, sizeof(double) * C, st));
+    if (mode == 2) INSMOS_CHECK_CUDA(cudaMemsetAsync(out1, 0, sizeof(double) * C, st));
+    if (n == 0) return INSMOS_OK;
+    int64_t blocks = 148 * 4;
+    int64_t rpb = ceil_div64(n, blocks);
+    if (rpb < 64) rpb = 64;
+    blocks = ceil_div64(n, rpb);
+    const int Cc = C <= CM_THREADS ? C : CM_THREADS;
+    const int RL = CM_THREADS / Cc > 0 ? CM_THREADS / Cc : 1;
+    const size_t smem = sizeof(double) * 2 * RL * Cc;
+    k_column_moments<<<(unsigned)blocks, CM_THREADS, smem, st>>>(a, b, gate, mean, invstd, n, C, mode, (int)rpb, out0, out1);
+    INSMOS_CHECK_LAUNCH("k_column_moments");
+    return INSMOS_OK;
+}
+
+// train-mode BatchNorm backward, elementwise part:  dx = coef[c] * (g - m0[c] - xhat * m1[c])  with g = dy gated by the ReLU
+// (gate > 0), xhat = (x - mean) * invstd, coef = gamma * invstd, m0 = sum(g)/n, m1 = sum(g * xhat)/n.
+__global__ void k_bn_bwd_apply(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gate,
+                               const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ coef,
+                               const float* __restrict__ m0, const float* __restrict__ m1, int64_t total, int C,
+                               float* __restrict__ dx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    float g = dy[i];
+    if (gate && !(gate[i] > 0.0f)) g = 0.0f;
+    const float xhat = (x[i] - mean[c]) * invstd[c];
+    dx[i] = coef[c] * (g - m0[c] - xhat * m1[c]);
+}
+
+extern "C" int insmos_bn_bwd_apply(const float* dy, const float* x, const float* gate, const float* mean, const float* invstd,
+                                   const float* coef, const float* m0, const float* m1, int64_t n, int32_t C, float* dx,
+                                   void* stream) {
+    if (C <= 0 || n < 0 || (n > 0 && (!dy || !x || !dx)) || !mean || !invstd || !coef || !m0 || !m1) return INSMOS_ERR_INVALID_ARG;
+    if (n == 0) return INSMOS_OK;
+    const int64_t total = n * C;
+    k_bn_bwd_apply<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(dy, x, gate, mean, invstd, coef, m0, m1, total, C, dx);
+    INSMOS_CHECK_LAUNCH("k_bn_bwd_apply");
+    return INSMOS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[idx[i], :] += src[i, :]  (idx < 0 skipped): backward of insmos_gather_rows / SparseTensor.slice /
+// gather_features_by_pc_voxel_id.  `out` must be initialised by the caller.  fp32 atomics: the summation order of the
+// points of one voxel varies between runs (a few ulps on the affected rows).
+__global__ void k_scatter_add_rows(const float* __restrict__ src, const int32_t* __restrict__ idx, int64_t n, int C, int ldsrc,
+                                   float* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * C) return;
+    const int64_t r = i / C;
+    const int c = (int)(i - r * C);
+    const int dst = idx[r];
+    if (dst >= 0) atomicAdd(out + (int64_t)dst * C + c, src[r * ldsrc + c]);
+}
+
+extern "C" int insmos_scatter_add_rows(const float* src, int32_t C, int32_t ldsrc, const int32_t* idx, int64_t n, float* out, void* stream) {
+    if (C <= 0 || ldsrc < C || n < 0 || (n > 0 && (!src || !idx || !out))) return INSMOS_ERR_INVALID_ARG;
+    if (n == 0) return INSMOS_OK;
+    k_scatter_add_rows<<<(unsigned)ceil_div64(n * C, 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n, C, ldsrc, out);
+    INSMOS_CHECK_LAUNCH("k_scatter_add_rows");
+    return INSMOS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CenterHead.get_targets_single (center_head.py:171-249) for one sample: one block per ground-truth box.
+// The reference walks the boxes in a Python loop (a device synchronisation per comparison); the heat map is a running
+// maximum, which commutes, so the boxes are drawn in parallel with atomicMax on the bit pattern of the non-negative floats.
+// Arithmetic follows the reference's dtypes: box sizes in fp32 (box / fp32 voxel / factor), gaussian_radius in fp32 with the
+// same operation order and no fused multiply-adds, the centre in fp32 when the configured range is integral (fp32 box - int64
+// range stays fp32 in torch; the reference's config.yaml lists integers) or in fp64 rounded to fp32 when it is not (fp32 -
+// fp64 promotes), then truncated; the Gaussian in fp64 (numpy) rounded to fp32.
+__device__ __forceinline__ float gaussian_radius_f32(float height, float width, float min_overlap) {
+    const float b1 = __fadd_rn(height, width);
+    const float c1 = __fdiv_rn(__fmul_rn(__fmul_rn(width, height), 1.0f - min_overlap), 1.0f + min_overlap);
+    const float sq1 = __fsqrt_rn(__fsub_rn(__fmul_rn(b1, b1), __fmul_rn(4.0f, c1)));
+    const float r1 = __fdiv_rn(__fadd_rn(b1, sq1), 2.0f);
+    const float b2 = __fmul_rn(2.0f, __fadd_rn(height, width));
+    const float c2 = __fmul_rn(__fmul_rn(1.0f - min_overlap, width), height);
+    const float sq2 = __fsqrt_rn(__fsub_rn(__fmul_rn(b2, b2), __fmul_rn(16.0f, c2)));
+    const float r2 = __fdiv_rn(__fadd_rn(b2, sq2), 2.0f);
+    const float a3 = 4.0f * min_overlap;
+    const float b3 = __fmul_rn(-2.0f * min_overlap, __fadd_rn(height, width));
+    const float c3 = __fmul_rn(__fmul_rn(min_overlap - 1.0f, width), height);
+    const float sq3 = __fsqrt_rn(__fsub_rn(__fmul_rn(b3, b3), __fmul_rn(__fmul_rn(4.0f, a3), c3)));
+    const float r3 = __fdiv_rn(__fadd_rn(b3, sq3), 2.0f);
+    return fminf(r1, fminf(r2, r3));
+}
+
+__global__ void k_center_targets(const float* __restrict__ gt, int n_box, int max_objs, int H, int W, int ncls, double x_min,
+                                 double y_min, int range_fp64, float vx, float vy, int factor, float min_overlap, int min_radius,
+                                 float* __restrict__ heatmap, float* __restrict__ anno, int64_t* __restrict__ ind,
+                                 uint8_t* __restrict__ mask) {
+    const int k = blockIdx.x;
+    if (k >= n_box || k >= max_objs) return;
+    const float* b = gt + (size_t)k * 8;
+    const int cls_id = (int)(b[7] - 1.0f);                              // (label - 1).int(): truncation
+    const float width = __fdiv_rn(__fdiv_rn(b[3], vx), (float)factor);
+    const float length = __fdiv_rn(__fdiv_rn(b[4], vy), (float)factor);
+    if (!(width > 0.0f && length > 0.0f && cls_id > -1) || cls_id >= ncls) return;
+    int radius = (int)gaussian_radius_f32(length, width, min_overlap);
+    if (radius < min_radius) radius = min_radius;
+    const float cxf = range_fp64 ? (float)((((double)b[0] - x_min) / (double)vx) / (double)factor)
+                                 : __fdiv_rn(__fdiv_rn(__fsub_rn(b[0], (float)x_min), vx), (float)factor);
+    const float cyf = range_fp64 ? (float)((((double)b[1] - y_min) / (double)vy) / (double)factor)
+                                 : __fdiv_rn(__fdiv_rn(__fsub_rn(b[1], (float)y_min), vy), (float)factor);
+    const int x = (int)cxf, y = (int)cyf;
+    if (!(0 <= x && x < W && 0 <= y && y < H)) return;
+    // draw_heatmap_gaussian (center_head.py:369-399): sigma = diameter / 6, window clipped to the map
+    const int diameter = 2 * radius + 1;
+    const double sigma = (double)diameter / 6.0;
+    const int left = min(x, radius), right = min(W - x, radius + 1), top = min(y, radius), bottom = min(H - y, radius + 1);
+    const int ww = left + right, hh = top + bottom;
+    int* hm = reinterpret_cast<int*>(heatmap + (size_t)cls_id * H * W);
+    for (int i = threadIdx.x; i < ww * hh; i += blockDim.x) {
+        const int dy = i / ww - top, dx = i % ww - left;
+        const float gval = (float)exp(-(double)(dx * dx + dy * dy) / (2.0 * sigma * sigma));
+        atomicMax(hm + (size_t)(y + dy) * W + (x + dx), __float_as_int(gval));
+    }
+    if (threadIdx.x == 0) {
+        ind[k] = (int64_t)y * W + x;
+        mask[k] = 1;
+        float* a = anno + (size_t)k * 8;
+        a[0] = cxf - (float)x; a[1] = cyf - (float)y; a[2] = b[2];
+        a[3] = logf(b[3]); a[4] = logf(b[4]); a[5] = logf(b[5]);
+        a[6] = sinf(b[6]); a[7] = cosf(b[6]);
+    }
+}
+
+extern "C" int insmos_center_targets(const float* gt_boxes, int32_t n_box, int32_t max_objs, int32_t H, int32_t W, int32_t ncls,
+                                     double x_min, double y_min, int32_t range_is_fp64, float vx, float vy, int32_t out_size_factor,
+                                     float min_overlap, int32_t min_radius, float* heatmap, float* anno_boxes, int64_t* inds,
+                                     uint8_t* masks, void* stream) {
+    if (n_box < 0 || max_objs <= 0 || H <= 0 || W <= 0 || ncls <= 0 || !heatmap || !anno_boxes || !inds || !masks ||
+        (n_box > 0 && !gt_boxes) || out_size_factor <= 0)
+        return INSMOS_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    INSMOS_CHECK_CUDA(cudaMemsetAsync(heatmap, 0, sizeof(float) * (size_t)ncls * H * W, st));
+    INSMOS_CHECK_CUDA(cudaMemsetAsync(anno_boxes, 0, sizeof(float) * (size_t)max_objs * 8, st));
+    INSMOS_CHECK_CUDA(cudaMemsetAsync(inds, 0, sizeof(int64_t) * (size_t)max_objs, st));
+    INSMOS_CHECK_CUDA(cudaMemsetAsync(masks, 0, (size_t)max_objs, st));
+    const int nb = n_box < max_objs ? n_box : max_objs;
+    if (nb == 0) return INSMOS_OK;
+    k_center_targets<<<nb, 128, 0, st>>>(gt_boxes, nb, max_objs, H, W, ncls, x_min, y_min, range_is_fp64, vx, vy, out_size_factor, min_overlap,
+                                          min_radius, heatmap, anno_boxes, inds, masks);
+    INSMOS_CHECK_LAUNCH("k_center_targets");
+    return INSMOS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// torch.optim.Adam (models.py:185-190: lr, weight_decay as L2 added to the gradient, betas 0.9 / 0.999, eps 1e-8) over ONE
+// flat fp32 buffer holding every parameter (the gradients live in a second flat buffer, so the data-parallel all-reduce is a
+// single NCCL call on it).  grad_scale folds the 1/world_size of the gradient average into the step.
+__global__ void k_adam_step(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1, float bc2_sqrt,
+                            float grad_scale) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float gi = g[i] * grad_scale;
+    const float pi = p[i];
+    if (weight_decay != 0.0f) gi = __fmaf_rn(weight_decay, pi, gi);
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+}
+
+extern "C" int insmos_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                                float beta2, float eps, float weight_decay, int64_t step, float grad_scale, void* stream) {
+    if (n < 0 || step < 1 || (n > 0 && (!param || !grad || !exp_avg || !exp_avg_sq))) return INSMOS_ERR_INVALID_ARG;
+    if (n == 0) return INSMOS_OK;
+    const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    k_adam_step<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                                                weight_decay, bc1, bc2_sqrt, grad_scale);
+    INSMOS_CHECK_LAUNCH("k_adam_step");
+    return INSMOS_OK;
+}

@@ -139,8 +139,24 @@ class BaseBEVBackbone(nn.Module):
         return data_dict
 
 
+def clip_sigmoid(x, eps=1e-4):
+    """center_head.py:333-345 (the reference applies the sigmoid in place; the values are the same)"""
+    return torch.clamp(torch.sigmoid(x), min=eps, max=1 - eps)
+
+
+def gaussian_focal_loss(pred, gaussian_target, alpha=2.0, gamma=4.0):
+    """center_head.py:590-611: element-wise focal loss against a Gaussian heat map (positives: target == 1)."""
+    eps = 1e-12
+    pos_weights = gaussian_target.eq(1)
+    neg_weights = (1 - gaussian_target).pow(gamma)
+    pos_loss = -(pred + eps).log() * (1 - pred).pow(alpha) * pos_weights
+    neg_loss = -(1 - pred + eps).log() * pred.pow(alpha) * neg_weights
+    return pos_loss + neg_loss
+
+
 class CenterHead(nn.Module):
-    """forward + box decoding only (target assignment and losses are training-only)."""
+    """forward + box decoding (center_head.py:65-98,251-276); in 'train' mode also target assignment on device
+    (insmos_center_targets replaces the Python loop of center_head.py:171-249) and the two losses (:279-331)."""
 
     def __init__(self, model_cfg, input_channels, num_class, class_names, grid_size, point_cloud_range,
                  predict_boxes_when_training=True):
@@ -166,12 +182,56 @@ class CenterHead(nn.Module):
             self._heads = (ver, w, b)
         return self._heads[1], self._heads[2]
 
+    def assign_targets(self, gt_boxes):
+        """gt_boxes [1, M, 8] (x,y,z,dx,dy,dz,yaw,class) -> dict of one-element lists, shapes as center_head.py:126-169:
+        heatmaps [1,ncls,H,W], anno_boxes [1,MAX_OBJS,8], inds int64 [1,MAX_OBJS], masks uint8 [1,MAX_OBJS]."""
+        if gt_boxes.dim() != 3 or gt_boxes.shape[0] != 1:
+            raise NotImplementedError("batch 1 per sample (models.py:313)")
+        t = self.target_cfg
+        f = int(t["OUT_SIZE_FACTOR"])
+        W, H = int(self.grid_size[0]) // f, int(self.grid_size[1]) // f
+        heat, anno, inds, masks = ops.center_targets(
+            gt_boxes[0].float().contiguous(), int(t["MAX_OBJS"]), H, W, len(self.class_names[0]),
+            float(self.point_cloud_range[0]), float(self.point_cloud_range[1]), float(t["VOXEL_SIZE"][0]), float(t["VOXEL_SIZE"][1]),
+            f, float(t["GAUSSIAN_OVERLAP"]), int(t["MIN_RADIUS"]),
+            range_is_fp64=not np.issubdtype(np.asarray(self.point_cloud_range).dtype, np.integer))
+        return {"heatmaps": [heat.unsqueeze(0)], "anno_boxes": [anno.unsqueeze(0)], "inds": [inds.unsqueeze(0)],
+                "masks": [masks.unsqueeze(0)]}
+
+    def get_cls_layer_loss(self):                                        # center_head.py:288-303
+        pred = clip_sigmoid(self.forward_ret_dict["cls_preds"]).permute(0, 3, 1, 2)
+        gt = self.forward_ret_dict["heatmaps"][0]
+        num_pos = gt.eq(1).float().sum().clamp(min=1.0)
+        w = self.model_cfg["LOSS_CONFIG"]["LOSS_WEIGHTS"]
+        cls_loss = gaussian_focal_loss(pred, gt).sum() / num_pos * w["cls_weight"]
+        return cls_loss, {"rpn_loss_cls": cls_loss.detach()}
+
+    def get_box_reg_layer_loss(self):                                    # center_head.py:306-331
+        target_box, inds, masks = (self.forward_ret_dict[k][0] for k in ("anno_boxes", "inds", "masks"))
+        num = masks.float().sum()
+        pred = self.forward_ret_dict["box_preds"]
+        pred = pred.view(pred.size(0), -1, pred.size(3))
+        pred = pred.gather(1, inds.unsqueeze(2).expand(inds.size(0), inds.size(1), pred.size(2)))
+        mask = masks.unsqueeze(2).expand_as(target_box).float() * (~torch.isnan(target_box)).float()
+        w = self.model_cfg["LOSS_CONFIG"]["LOSS_WEIGHTS"]
+        bbox_weights = mask * mask.new_tensor(w["code_weights"])
+        loc_loss = (torch.abs(pred - target_box) * bbox_weights).sum() / (num + 1e-4) * w["loc_weight"]
+        return loc_loss, {"rpn_loss_loc": loc_loss.detach()}
+
+    def get_loss(self):                                                  # center_head.py:279-286 (values stay on the device)
+        cls_loss, tb = self.get_cls_layer_loss()
+        box_loss, tb_box = self.get_box_reg_layer_loss()
+        tb.update(tb_box)
+        rpn_loss = cls_loss + box_loss
+        tb["rpn_loss"] = rpn_loss.detach()
+        return rpn_loss, tb
+
     def forward(self, data_dict, Model_mode):
-        if Model_mode == "train":
-            raise NotImplementedError("CenterHead target assignment / losses are training-only (out of scope, SURVEY 8f N3)")
         t = self.target_cfg
         dec = (t["OUT_SIZE_FACTOR"], t["VOXEL_SIZE"][0], t["VOXEL_SIZE"][1], self.point_cloud_range[0], self.point_cloud_range[1])
         nhwc = data_dict.get("spatial_features_2d_nhwc")
+        if Model_mode == "train" and nhwc is not None:
+            raise RuntimeError("CenterHead: 'train' mode needs the module in training mode (model.train())")
         if nhwc is not None:
             x, H, W = nhwc
             w, b = self._fused_heads()
@@ -185,8 +245,12 @@ class CenterHead(nn.Module):
             box = self.conv_box(x)                                         # [1, 8, H, W]
             if cls.shape[0] != 1:
                 raise NotImplementedError("batch 1 per sample (models.py:313)")
-            boxes, scores, labels = ops.center_decode(cls[0], box[0], *dec)
-            data_dict["batch_cls_preds"] = cls[0].permute(1, 2, 0).reshape(1, -1, self.num_class)
+            if Model_mode == "train":                                      # center_head.py:72-90
+                self.forward_ret_dict["cls_preds"] = cls.permute(0, 2, 3, 1).contiguous()
+                self.forward_ret_dict["box_preds"] = box.permute(0, 2, 3, 1).contiguous()
+                self.forward_ret_dict.update(self.assign_targets(data_dict["gt_boxes"]))
+            boxes, scores, labels = ops.center_decode(cls[0].detach(), box[0].detach(), *dec)
+            data_dict["batch_cls_preds"] = cls[0].detach().permute(1, 2, 0).reshape(1, -1, self.num_class)
         data_dict["batch_box_preds"] = boxes.unsqueeze(0)
         data_dict["cls_preds_normalized"] = False
         data_dict["_decoded"] = (boxes, scores, labels)                     # sigmoid / class max already done on device

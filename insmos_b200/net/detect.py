@@ -58,4 +58,6 @@ class InstanceBoxes:
         n, c = features.shape
         bits = torch.zeros((n, self.PAD), dtype=torch.float32, device=features.device)
         ops.box_membership(indices, self.boxes8, float(mult), out=bits, out_stride=self.PAD, col_offset=0, n_class=self.num_class)
+        if torch.is_grad_enabled() and features.requires_grad:
+            return torch.cat([features, bits], 1), bits
         return ops.concat2(features, bits), bits

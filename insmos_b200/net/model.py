@@ -70,7 +70,12 @@ class MOSLoss(nn.Module):
         self.loss = _NLLWeight(torch.Tensor([x / sum(w) for x in w]))
 
     def compute_loss(self, out, past_labels):
-        raise NotImplementedError("training losses are out of scope for the forward path (SURVEY 8f N3)")
+        """loss.py:20-34: ignored classes to -inf (written into `out` in place, as the reference does), softmax, log of the
+        clamped probabilities, class-weighted NLL."""
+        logits = out
+        logits[:, self.ignore_index] = -float("inf")
+        log_softmax = torch.log(torch.softmax(logits, dim=1).clamp(min=1e-8))
+        return torch.nn.functional.nll_loss(log_softmax, past_labels.long(), weight=self.loss.weight)
 
 
 class InsMOS_Model(nn.Module):
@@ -94,12 +99,13 @@ class InsMOS_Model(nn.Module):
         self.use_motion_loss = M["USE_MOTION_LOSS"]
 
     def forward(self, list_batch_dict, Model_mode):
+        if Model_mode == "train":
+            return self.forward_train(list_batch_dict)
         if Model_mode != "test":
-            # 'train' needs target assignment, losses and backward kernels; 'eval' returns the validation losses and the
-            # per-sample recall records of generate_recall_record (models/models.py:331-359), which depend on the same
-            # training-side code.  Returning NaN losses / empty recall dicts would let a reference validation_step log
-            # garbage silently, so both modes refuse.
-            raise NotImplementedError("Model_mode %r: only the inference forward ('test') is implemented (SURVEY 8f N3)" % Model_mode)
+            # 'eval' returns the per-sample recall records of generate_recall_record (models/models.py:331-359), which need
+            # boxes_iou3d_gpu (not built).  Returning empty recall dicts would let a reference validation_step log garbage
+            # silently, so the mode refuses.
+            raise NotImplementedError("Model_mode %r: 'test' (inference) and 'train' are implemented" % Model_mode)
         boxes_out, recall_out, logits_out = [], [], []
         for batch_dict in list_batch_dict:
             batch_dict = self.motion_encoder(batch_dict)
@@ -112,6 +118,34 @@ class InsMOS_Model(nn.Module):
             recall_out.append(recall_dicts)
             logits_out.append(point_seg)
         return boxes_out, recall_out, logits_out
+
+
+def _forward_train(self, list_batch_dict):
+    """models/models.py:297-347,366-368: per sample  loss_rpn + loss_mos + loss_motion_encoder, averaged over the list.
+    The loss dictionary values stay 0-dim device tensors (the reference calls .item() on each: five host syncs per sample)."""
+    if not self.training:
+        raise RuntimeError("Model_mode 'train' needs model.train() (batch statistics, torch BEV modules)")
+    dev = list_batch_dict[0]["past_point_clouds"].device
+    loss = torch.zeros(1, device=dev)
+    train_loss_dict, gt_list, pred_list = [], [], []
+    for batch_dict in list_batch_dict:
+        batch_dict = self.motion_encoder(batch_dict)
+        if not self.use_motion_loss:
+            batch_dict["current_motion_feature"] = batch_dict["current_motion_feature"][:, :3]
+        gt = batch_dict["past_labels"][-1]
+        loss_motion = self.MOSLoss.compute_loss(batch_dict["current_motion_feature"], gt)
+        batch_dict = self.voxel_generate(batch_dict)
+        batch_dict = self.vfe(batch_dict)
+        (loss_rpn, tb), point_seg = self.unet(batch_dict, "train")
+        loss_mos = self.MOSLoss.compute_loss(point_seg, gt)
+        loss = loss + loss_rpn + loss_mos + (loss_motion if self.use_motion_loss else 0.0)
+        train_loss_dict.append({"loss_mos": loss_mos.detach(), "loss_motion_encoder": loss_motion.detach(), **tb})
+        gt_list.append(gt)
+        pred_list.append(point_seg)
+    return loss / len(list_batch_dict), train_loss_dict, gt_list, pred_list
+
+
+InsMOS_Model.forward_train = _forward_train
 
 
 class ClassificationMetrics(nn.Module):

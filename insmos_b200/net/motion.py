@@ -10,7 +10,7 @@ import torch.nn as nn
 import MinkowskiEngine as ME
 from MinkowskiEngine.modules.resnet_block import BasicBlock
 
-from insmos_b200 import ops
+from insmos_b200 import autograd, ops
 
 
 class CustomMinkUNet(nn.Module):
@@ -77,7 +77,7 @@ class CustomMinkUNet(nn.Module):
     def _cbr(self, conv, bn, x):
         """conv -> BatchNorm -> ReLU; one fused kernel in eval mode."""
         if self.training:
-            return self.relu(bn(conv(x)))
+            return bn(conv(x), relu=True)
         return conv(x, bn=bn, relu=True)
 
     def forward(self, x):                                       # minkunet.py:139-181
@@ -121,8 +121,18 @@ class MotionNet(nn.Module):
         feats = torch.full((voxels.n, 1), 0.5, dtype=torch.float32, device=pts.device)
         pred = self.MinkUNet(ME.SparseTensor(feats, coordinate_manager=mgr, coordinate_map_key=key))
         # a5: slice back to points, keep the current scan, hstack(x,y,z,intensity, motion logits)
-        cur = ops.build_current_points(pts, cur_index, inverse, pred.F, self.out_channels)
-        batch_dict["current_point"] = cur
-        batch_dict["current_motion_feature"] = cur[:, 4:]
+        if autograd.needs_grad(pred.F):
+            # training: the motion logits stay attached to the graph (loss_motion_encoder, models.py:321-324); the point
+            # columns carry no gradient.  current_point is detached below exactly where the reference's PointToVoxel cuts
+            # the graph (voxel_generate.py:27: spconv's voxel generator is not an autograd op)
+            cur_inv = inverse.index_select(0, cur_index.long()).contiguous()
+            motion = autograd.gather_rows(pred.F[:, :self.out_channels].contiguous(), cur_inv)
+            cur = torch.cat([pts.index_select(0, cur_index.long())[:, :4], motion.detach()], 1).contiguous()
+            batch_dict["current_point"] = cur
+            batch_dict["current_motion_feature"] = motion
+        else:
+            cur = ops.build_current_points(pts, cur_index, inverse, pred.F, self.out_channels)
+            batch_dict["current_point"] = cur
+            batch_dict["current_motion_feature"] = cur[:, 4:]
         batch_dict["_motion_stats"] = {"n_points": pts.shape[0], "n_voxels4d": voxels.n, "manager": mgr}
         return batch_dict

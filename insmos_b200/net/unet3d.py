@@ -14,7 +14,7 @@ import torch.nn as nn
 import spconv.pytorch as spconv
 from spconv.pytorch.utils import gather_features_by_pc_voxel_id
 
-from insmos_b200 import ops
+from insmos_b200 import autograd, ops
 from .bev import BaseBEVBackbone, CenterHead, HeightCompression
 from .detect import InstanceBoxes, post_processing
 
@@ -34,11 +34,11 @@ class SparseBasicBlock(spconv.SparseModule):
     def forward(self, x):
         if self.training:
             out = self.conv1(x)
-            out = out.replace_feature(self.relu(self.bn1(out.features)))
+            out = out.replace_feature(autograd.batch_norm_train(self.bn1, out.features, relu=True))
             out = self.conv2(out)
-            out = out.replace_feature(self.bn2(out.features))
+            out = out.replace_feature(autograd.batch_norm_train(self.bn2, out.features))
             identity = x.features if self.downsample is None else self.downsample(x).features
-            return out.replace_feature(self.relu(out.features + identity))
+            return out.replace_feature(torch.relu(out.features + identity))
         identity = x.features if self.downsample is None else self.downsample(x).features
         out = self.conv1(x, bn=self.bn1, relu=True)
         return self.conv2(out, bn=self.bn2, residual=identity, relu=True)
@@ -126,6 +126,11 @@ class UNetV2(nn.Module):
     def ur_block(x_lateral, x_bottom, conv_t, conv_m, conv_inv):
         """spconv_unet.py:213-238: transform lateral, concat with bottom, merge conv + pair-sum skip, inverse conv."""
         x_trans = conv_t(x_lateral)
+        if autograd.needs_grad(x_bottom.features, x_trans.features):        # training: plain torch glue keeps the graph
+            cat = torch.cat((x_bottom.features, x_trans.features), dim=1)
+            x_m = conv_m(x_trans.replace_feature(cat))
+            red = cat.view(cat.shape[0], x_m.features.shape[1], -1).sum(dim=2)
+            return conv_inv(x_m.replace_feature(x_m.features + red))
         cat = ops.concat2(x_bottom.features, x_trans.features)
         x_m = conv_m(x_trans.replace_feature(cat))
         assert cat.shape[1] == 2 * x_m.features.shape[1]
@@ -176,28 +181,39 @@ class UNetV2(nn.Module):
         # ---- upsample fusion with per-level instance bits (Array_Index on device)
         inst = InstanceBoxes(fuse_from, self.point_cloud_range[0:3], self.voxel_size,
                              batch_dict["encoded_spconv_tensor_stride"], self.num_class)
+        def with_bits(t, mult, bits=None):
+            """features + instance bits; in training the tensor remembers how many leading columns carry a gradient"""
+            c = t.features.shape[1]
+            if bits is None:
+                f, bits = inst.concat_bits(t.features, t.indices, mult)
+            else:
+                f = torch.cat([t.features, bits], 1) if autograd.needs_grad(t.features) else ops.concat2(t.features, bits)
+            r = t.replace_feature(f)
+            r.grad_cols = c
+            return r, bits
+
         inv_bev = self.inv_conv_out(out)
-        f, _ = inst.concat_bits(inv_bev.features, inv_bev.indices, 1)
-        x_inst = self.conv_up_instance_block(inv_bev.replace_feature(f))
+        x_inst = self.conv_up_instance_block(with_bits(inv_bev, 1)[0])
         x_up4 = self.ur_block(x_inst, x_inst, self.conv_up_t4, self.conv_up_m4, self.inv_conv4)
 
-        f, _ = inst.concat_bits(x_up4.features, x_up4.indices, 2)
-        x_up4_inst = self.conv_up_instance_block_up4(x_up4.replace_feature(f))
+        x_up4_inst = self.conv_up_instance_block_up4(with_bits(x_up4, 2)[0])
         x_up3 = self.ur_block(x_conv3, x_up4_inst, self.conv_up_t3, self.conv_up_m3, self.inv_conv3)
 
-        f, _ = inst.concat_bits(x_up3.features, x_up3.indices, 4)
-        x_up3_inst = self.conv_up_instance_block_up3(x_up3.replace_feature(f))
+        x_up3_inst = self.conv_up_instance_block_up3(with_bits(x_up3, 4)[0])
         x_up2 = self.ur_block(x_conv2, x_up3_inst, self.conv_up_t2, self.conv_up_m2, self.inv_conv2)
 
-        f, bits1 = inst.concat_bits(x_up2.features, x_up2.indices, 8)
-        x_up2_inst = self.conv_up_instance_block_up2(x_up2.replace_feature(f))
+        x_up2_b, bits1 = with_bits(x_up2, 8)
+        x_up2_inst = self.conv_up_instance_block_up2(x_up2_b)
         x_up1 = self.ur_block(x_conv1, x_up2_inst, self.conv_up_t1, self.conv_up_m1, self.conv_up_out)
 
         # the finest level re-uses the bits computed for x_up2 (same voxel rows): spconv_unet.py:401
-        x_up1_inst = self.conv_up_instance_block_up1(x_up1.replace_feature(ops.concat2(x_up1.features, bits1)))
+        x_up1_inst = self.conv_up_instance_block_up1(with_bits(x_up1, 8, bits1)[0])
 
-        seg = ops.linear(x_up1_inst.features, self.mos_seg_layer.weight.t().contiguous(), bias=self.mos_seg_layer.bias)
+        if autograd.needs_grad(x_up1_inst.features, self.mos_seg_layer.weight):
+            seg = autograd.linear(x_up1_inst.features, self.mos_seg_layer.weight.t(), self.mos_seg_layer.bias)
+        else:
+            seg = ops.linear(x_up1_inst.features, self.mos_seg_layer.weight.t().contiguous(), bias=self.mos_seg_layer.bias)
         point_seg = gather_features_by_pc_voxel_id(seg, batch_dict["list_pc_voxel_id"][-1])
         if Model_mode == "train":
-            raise NotImplementedError("training losses are out of scope for the forward path (SURVEY 8f N3)")
+            return self.center_head.get_loss(), point_seg                   # spconv_unet.py:413-414
         return point_seg, pred_dicts, recall_dicts

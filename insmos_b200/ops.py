@@ -810,3 +810,76 @@ def mos_labels(logits, ignore_mask, label_map=None, want_confidence=True):
     conf = torch.empty((n, Cc - 1), dtype=F32, device=logits.device) if want_confidence else None
     call("insmos_mos_labels", _p(logits), n, Cc, int(ignore_mask), _p(label_map), _p(labels), _p(conf), _stream())
     return labels, conf
+
+
+# ---- training step: the pieces without a forward counterpart ------------------------------------------
+def sparse_conv_wgrad(feat, dout, rb, K, Cin, Cout):
+    """dW[K,Cin,Cout] = sum over rule-book pairs (k, i, o) of feat[i]^T dout[o]  (deterministic slice-ordered reduction)."""
+    feat = _req(feat, F32, "sparse_conv_wgrad")
+    dout = _req(dout, F32, "sparse_conv_wgrad")
+    if feat.shape != (rb.n_in, Cin) or dout.shape != (rb.n_out, Cout) or K != rb.K:
+        raise ValueError("sparse_conv_wgrad: shape mismatch (feat %s, dout %s, rule book K=%d n_in=%d n_out=%d)"
+                         % (tuple(feat.shape), tuple(dout.shape), rb.K, rb.n_in, rb.n_out))
+    S = int(_lib.load().insmos_sparse_conv_wgrad_slices(rb.n_out, rb.TM, K, Cin))
+    partial = torch.empty((S, K, Cin, Cout), dtype=F32, device=feat.device)
+    dw = torch.empty((K, Cin, Cout), dtype=F32, device=feat.device)
+    if _lib.PROFILE is not None:
+        P = rb.num_pairs
+        _lib.NEXT_META = {"bytes": 4 * (rb.n_in * Cin + rb.n_out * Cout) + 8 * P + 4 * K * Cin * Cout,
+                          "flops": 2 * P * Cin * Cout, "pairs": P, "K": K, "Cin": Cin, "Cout": Cout, "n_out": rb.n_out}
+    call("insmos_sparse_conv_wgrad", _p(feat), rb.n_in, Cin, _p(dout), rb.n_out, Cout, _p(rb.seg), _p(rb.entries), rb.TM, K,
+         _p(partial), S, _p(dw), _stream())
+    return dw
+
+
+def scatter_add_rows(src, idx, n_rows):
+    """out[idx[i]] += src[i] over a zero [n_rows, C] matrix (idx < 0 skipped): backward of gather_rows."""
+    idx = _req(idx, I32, "scatter_add_rows")
+    if not src.is_cuda or src.dtype != F32 or src.stride(1) != 1:
+        src = _req(src, F32, "scatter_add_rows")
+    n, Cc = src.shape
+    out = torch.zeros((n_rows, Cc), dtype=F32, device=src.device)
+    call("insmos_scatter_add_rows", _p(src), Cc, src.stride(0) if n > 1 else Cc, _p(idx), n, _p(out), _stream())
+    return out
+
+
+def column_moments(a, mode, b=None, gate=None, mean=None, invstd=None):
+    """fp64 column sums over [n,C]: mode 0 sum(a); 1 sum((a-mean)^2); 2 (sum(g), sum(g*(b-mean)*invstd)), g = a gated by gate>0."""
+    a = _req(a, F32, "column_moments")
+    n, Cc = a.shape
+    out0 = torch.empty(Cc, dtype=torch.float64, device=a.device)
+    out1 = torch.empty(Cc, dtype=torch.float64, device=a.device) if mode == 2 else None
+    call("insmos_column_moments", _p(a), _p(b), _p(gate), _p(mean), _p(invstd), n, Cc, int(mode), _p(out0), _p(out1), _stream())
+    return out0 if mode != 2 else (out0, out1)
+
+
+def bn_bwd_apply(dy, x, gate, mean, invstd, coef, m0, m1):
+    dy = _req(dy, F32, "bn_bwd_apply")
+    n, Cc = dy.shape
+    dx = torch.empty_like(dy)
+    call("insmos_bn_bwd_apply", _p(dy), _p(x), _p(gate), _p(mean), _p(invstd), _p(coef), _p(m0), _p(m1), n, Cc, _p(dx), _stream())
+    return dx
+
+
+def center_targets(gt_boxes, max_objs, H, W, ncls, x_min, y_min, vx, vy, out_size_factor, min_overlap, min_radius, range_is_fp64=False):
+    """CenterHead.get_targets_single on device: gt_boxes [M,8] -> heatmap [ncls,H,W], anno_boxes [max_objs,8],
+    inds int64 [max_objs], masks uint8 [max_objs]."""
+    gt_boxes = _req(gt_boxes, F32, "center_targets")
+    dev = gt_boxes.device
+    heat = torch.empty((ncls, H, W), dtype=F32, device=dev)
+    anno = torch.empty((max_objs, 8), dtype=F32, device=dev)
+    inds = torch.empty(max_objs, dtype=torch.int64, device=dev)
+    masks = torch.empty(max_objs, dtype=torch.uint8, device=dev)
+    call("insmos_center_targets", _p(gt_boxes), gt_boxes.shape[0], int(max_objs), int(H), int(W), int(ncls), float(x_min),
+         float(y_min), 1 if range_is_fp64 else 0, float(vx), float(vy), int(out_size_factor), float(min_overlap), int(min_radius), _p(heat), _p(anno),
+         _p(inds), _p(masks), _stream())
+    return heat, anno, inds, masks
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    """in-place torch.optim.Adam step over flat fp32 buffers."""
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        if not (t.is_cuda and t.dtype == F32 and t.is_contiguous() and t.numel() == param.numel()):
+            raise ValueError("adam_step: flat contiguous float32 CUDA buffers of equal length required")
+    call("insmos_adam_step", _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), param.numel(), float(lr), float(beta1), float(beta2),
+         float(eps), float(weight_decay), int(step), float(grad_scale), _stream())

@@ -25,6 +25,8 @@ PP = {"SCORE_THRESH": 0.1, "NMS_THRESH": 0.01, "NMS_PRE_MAXSIZE": 4096, "NMS_POS
 
 
 def _bn(sd, p, x, eps):
+    if sd.get("__train__") is not None:                  # training step (oracle/train.py): batch statistics, as model.train() does
+        return F.batch_norm(x, None, None, sd[p + ".weight"], sd[p + ".bias"], True, 0.0, eps)
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"], False, 0.0, eps)
 
 
@@ -185,11 +187,14 @@ def bev_head(sd, p, spatial):
     xs = xs * 4 * 0.1 + PC_RANGE[0]
     ys = ys * 4 * 0.1 + PC_RANGE[1]
     boxes = torch.cat([xs, ys, bp[..., 2:3], torch.exp(bp[..., 3:6]), torch.atan2(bp[..., 6:7], bp[..., 7:8])], dim=2)
+    if sd.get("__train__") is not None:                  # raw head outputs for the losses (center_head.py:72-76)
+        sd["__train__"]["cls_preds"], sd["__train__"]["box_preds"] = cls, box
     return cls.view(b, H * W, -1), boxes
 
 
 def post_process(cls_preds, box_preds):
     """post_process.py:112-224 + class_agnostic_nms :5-24 + nms_gpu"""
+    cls_preds, box_preds = cls_preds.detach(), box_preds.detach()       # (no-op at inference; the training oracle carries a graph)
     scores, labels = torch.max(torch.sigmoid(cls_preds[0]), dim=-1)
     labels = labels + 1
     boxes = box_preds[0]

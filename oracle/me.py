@@ -17,6 +17,11 @@ import torch
 _B = 1 << 15
 
 
+# dtype of the FEATURE arithmetic (coordinates are always quantised in fp32).  oracle/train.py switches it to float64 to obtain
+# reference gradients free of fp32 rounding (tests/golden/make_golden_train_f64.py)
+FDTYPE = torch.float32
+
+
 def pack_keys(coords):
     """int64 key of int rows (batch, c0, c1, c2[, c3]); |c0..c2| < 2^15, |c3| < 128, batch < 127."""
     c = np.asarray(coords).astype(np.int64)
@@ -62,11 +67,11 @@ def quantize_points(points_xyzt, quant):
 
 def segment_mean(feats, inverse, n_rows):
     """UNWEIGHTED_AVERAGE quantisation of TensorField.sparse()."""
-    feats = torch.as_tensor(feats, dtype=torch.float32)
+    feats = torch.as_tensor(feats, dtype=FDTYPE)
     inv = torch.as_tensor(inverse, dtype=torch.int64)
-    out = torch.zeros((n_rows, feats.shape[1]), dtype=torch.float32)
+    out = torch.zeros((n_rows, feats.shape[1]), dtype=FDTYPE)
     out.index_add_(0, inv, feats)
-    cnt = torch.bincount(inv, minlength=n_rows).clamp_min(1).to(torch.float32)
+    cnt = torch.bincount(inv, minlength=n_rows).clamp_min(1).to(FDTYPE)
     return out / cnt[:, None]
 
 
@@ -138,19 +143,19 @@ def transpose_map(maps):
 
 def conv(feats, weight, maps, n_out, bias=None):
     """gather -> mm -> scatter-add per kernel offset (ME CPU algorithm).  weight [K,Cin,Cout] or [Cin,Cout]."""
-    feats = torch.as_tensor(feats, dtype=torch.float32)
-    W = torch.as_tensor(weight, dtype=torch.float32)
+    feats = torch.as_tensor(feats, dtype=FDTYPE)
+    W = torch.as_tensor(weight, dtype=FDTYPE)
     if W.dim() == 2:
         out = feats @ W
     else:
-        out = torch.zeros((n_out, W.shape[2]), dtype=torch.float32)
+        out = torch.zeros((n_out, W.shape[2]), dtype=FDTYPE)
         for k, (i, o) in enumerate(maps):
             if len(i) == 0:
                 continue
             out.index_add_(0, torch.from_numpy(np.asarray(o, dtype=np.int64)),
                            feats.index_select(0, torch.from_numpy(np.asarray(i, dtype=np.int64))) @ W[k])
     if bias is not None:
-        out = out + torch.as_tensor(bias, dtype=torch.float32).reshape(1, -1)
+        out = out + torch.as_tensor(bias, dtype=FDTYPE).reshape(1, -1)
     return out
 
 

@@ -97,6 +97,11 @@ class MinkowskiReLU(nn.Module):
         return x._like(torch.relu(x.F))
 
 
+def _live(p):
+    """parameters stay attached to autograd when a training golden is being made (tests/golden/make_golden_train.py)"""
+    return p if (torch.is_grad_enabled() and p.requires_grad) else p.detach()
+
+
 class _Conv(nn.Module):
     transposed = False
 
@@ -112,14 +117,14 @@ class _Conv(nn.Module):
     def forward(self, x):
         mgr, in_key = x.coordinate_manager, x.coordinate_map_key
         if self.kernel_volume == 1 and all(s == 1 for s in self.stride):
-            return x._like(me.conv(x.F, self.kernel.detach(), None, len(x.F), bias=None if self.bias is None else self.bias.detach()))
+            return x._like(me.conv(x.F, _live(self.kernel), None, len(x.F), bias=None if self.bias is None else _live(self.bias)))
         if not self.transposed:
             out_key = in_key if all(s == 1 for s in self.stride) else mgr.stride(in_key, self.stride)
             maps = mgr.kernel_map(in_key, out_key, self.kernel_size)
         else:
             out_key = tuple(k // s for k, s in zip(in_key, self.stride))
             maps = me.transpose_map(mgr.kernel_map(out_key, in_key, self.kernel_size))
-        f = me.conv(x.F, self.kernel.detach(), maps, len(mgr.sets[out_key]), bias=None if self.bias is None else self.bias.detach())
+        f = me.conv(x.F, _live(self.kernel), maps, len(mgr.sets[out_key]), bias=None if self.bias is None else _live(self.bias))
         return x._like(f, out_key)
 
 

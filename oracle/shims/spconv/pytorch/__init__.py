@@ -72,7 +72,7 @@ class SparseConvolution(SparseModule):
                 d = {"maps": maps, "in_ind": ind, "in_shape": x.spatial_shape, "out_ind": oind, "out_shape": oshape}
                 x.indice_dict[self.indice_key] = d
             maps, out_ind, out_shape = d["maps"], d["out_ind"], d["out_shape"]
-        f = sp.conv(x.features, self.weight.detach(), maps, len(out_ind))
+        f = sp.conv(x.features, (self.weight if (torch.is_grad_enabled() and self.weight.requires_grad) else self.weight.detach()), maps, len(out_ind))
         return SparseConvTensor(f, torch.from_numpy(np.ascontiguousarray(out_ind)), out_shape, x.batch_size, x.indice_dict)
 
 

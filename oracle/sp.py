@@ -120,24 +120,24 @@ def sparse_conv_indices(indices, in_shape, ksize, stride, pad):
 
 def conv(feats, weight, maps, n_out):
     """weight in spconv layout [Cout,kz,ky,kx,Cin]."""
-    W = torch.as_tensor(weight, dtype=torch.float32)
+    W = torch.as_tensor(weight, dtype=me.FDTYPE)
     Cout, Cin = W.shape[0], W.shape[-1]
     Wk = W.reshape(Cout, -1, Cin).permute(1, 2, 0).contiguous()                          # [K,Cin,Cout]
     return me.conv(feats, Wk, maps, n_out)
 
 
 def dense(features, indices, spatial_shape, batch_size=1):
-    f = torch.as_tensor(features, dtype=torch.float32)
+    f = torch.as_tensor(features, dtype=me.FDTYPE)
     ind = torch.as_tensor(np.asarray(indices), dtype=torch.int64)
-    out = torch.zeros((batch_size, f.shape[1], *spatial_shape), dtype=torch.float32)
+    out = torch.zeros((batch_size, f.shape[1], *spatial_shape), dtype=me.FDTYPE)
     out[ind[:, 0], :, ind[:, 1], ind[:, 2], ind[:, 3]] = f
     return out
 
 
 def gather_features_by_pc_voxel_id(seg, ids):
-    seg = torch.as_tensor(seg, dtype=torch.float32)
+    seg = torch.as_tensor(seg, dtype=me.FDTYPE)
     ids = torch.as_tensor(np.asarray(ids), dtype=torch.int64)
-    out = torch.zeros((len(ids), seg.shape[1]), dtype=torch.float32)
+    out = torch.zeros((len(ids), seg.shape[1]), dtype=me.FDTYPE)
     m = ids >= 0
     out[m] = seg[ids[m]]
     return out

@@ -134,7 +134,9 @@ def test_lightning_checkpoint_loads_strictly_through_the_reference_call(dropin):
         assert torch.equal(got[k], sd[k])
     assert model.hparams["MODEL"]["DENSE_HEAD"]["NUM_CLASS"] == 3
     with pytest.raises(NotImplementedError):
-        model.forward([], "train")
+        model.forward([], "eval")                              # recall records need boxes_iou3d_gpu: refuses instead of logging garbage
+    with pytest.raises(RuntimeError):
+        model.forward([], "train")                             # 'train' is implemented (N3) but needs model.train()
     with pytest.raises(RuntimeError):                          # no CPU fallback: the script's .cuda() is mandatory
         model.forward([{"meta": None, "past_point_clouds": torch.zeros((4, 5)), "batch_size_npast": N_PAST}], "test")
 
