@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- scans/sec of the InsMOS sparse-voxel forward path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4|train]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 A step = one InsMOSNet.forward(batch, 'test') over one synthetic sample of BASELINE config C2:
@@ -18,6 +18,7 @@ the BatchNorm statistics of tests/golden/insmos_c2.npz -- the exact weights and 
 --impl reference: the CPU port timed alone on the FULL C2 cloud (the reference itself cannot run here: MinkowskiEngine /
 spconv are un-vendored externals); as many steps as fit the time budget, reported truthfully; rank 0 only.
 --workload c4: BASELINE config 4 (300 k points per scan, voxel 0.05 m): rule-book build + gather/scatter sweep line.
+--workload train: BASELINE config 5 (training step: forward + backward + gradient all-reduce + Adam on C2 samples with boxes / labels).
 Multi-GPU: samples sharded one per GPU (weak scaling), one fixed-size NCCL all_gather of the logits per step, no host sync.
 """
 import argparse
@@ -213,6 +214,110 @@ def run_c4(args, device, out_stream):
     out_stream.flush()
 
 
+def run_train(args, device, rank, local_rank, world, out_stream):
+    """BASELINE config 5: one TRAINING step per sample of the C2 workload (+ synthetic boxes and per-point MOS labels):
+    forward in train mode, losses, backward through this repository's gradient kernels, ONE NCCL all-reduce of the flat
+    gradient buffer, fused Adam.  Weak scaling: every rank trains on its own sample, weights replicated ("ZeRO-0 DDP")."""
+    import gc
+    from insmos_b200 import _lib, synth
+    from insmos_b200.config import default_config
+    from insmos_b200.train import TrainStep
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    n_clouds = 3
+    batches = []
+    for i in range(n_clouds):
+        pts, labels, boxes = synth.make_sequence(seed=100 * rank + i, n_scans=N_SCANS, n_elev=N_ELEV, n_azim=N_AZIM, return_labels=True)
+        batches.append((torch.from_numpy(pts).to(device), torch.from_numpy(labels.astype(np.float32)).to(device),
+                        torch.from_numpy(boxes).unsqueeze(0).to(device)))
+    net = build_model(device).train()
+    ts = TrainStep.from_config(net, default_config())
+
+    def batch(i):
+        pts, labels, boxes = batches[i % n_clouds]
+        return [{"meta": None, "past_point_clouds": pts, "past_labels": [labels], "gt_boxes": boxes, "batch_size_npast": N_SCANS}]
+
+    warmup = max(args.warmup, 12)         # the caching allocator / cuDNN settle after ~10 steps (measured: 90-110 ms, then 45 ms)
+    losses = [ts.step(batch(i)) for i in range(warmup)]
+    gc.collect()
+    gc.disable()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    launches0 = _lib.launch_count()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    walls, t_prev = [], time.perf_counter()
+    for i in range(args.steps):
+        last = ts.step(batch(warmup + i))                 # (returns python floats: one read-back = one sync per step)
+        t_now = time.perf_counter()
+        walls.append(round((t_now - t_prev) * 1000, 2))
+        t_prev = t_now
+    e.record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - launches0
+    sampler.stop_flag = True
+    gc.enable()
+    ms = torch.tensor([s.elapsed_time(e)], device=device)
+    if dist:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    ms = float(ms.item())
+    # per-family breakdown of one instrumented step (CUDA events around every C-ABI call; torch kernels show up as gaps)
+    _lib.profile_start()
+    t0 = time.perf_counter()
+    ts.step(batch(0))
+    prof = _lib.profile_stop()
+    prof_ms = (time.perf_counter() - t0) * 1000
+    if args.dump_launches and rank == 0:
+        with open(args.dump_launches, "w") as fh:
+            for name, t, m in prof:
+                fh.write(json.dumps({"call": name, "ms": round(t, 4), **(m or {})}) + "\n")
+    fam = {}
+    for name, t, meta in prof:
+        f = fam.setdefault(name, {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0})
+        f["ms"] += t
+        f["launches"] += 1
+        if meta:
+            f["bytes"] += meta.get("bytes", 0)
+            f["flops"] += meta.get("flops", 0)
+    peak, peak_src = peaks()
+    wg = fam.get("insmos_sparse_conv_wgrad", {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0})
+    kernels = {k: {"ms_per_step": round(v["ms"], 4), "launch_calls": v["launches"],
+                   "alg_GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["bytes"] and v["ms"] > 0 else None,
+                   "gflop": round(v["flops"] / 1e9, 2) if v["flops"] else None}
+               for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+    if rank == 0:
+        ach = wg["bytes"] / (wg["ms"] * 1e-3) / 1e9 if wg["ms"] > 0 else 0.0
+        line = {
+            "metric": "train_scans_per_sec", "value": round(world * args.steps / (ms / 1000.0), 3), "unit": "scans/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C5: training step on C2 samples (N=10 x 120k pts) + synthetic boxes [1,3,8] and per-point MOS labels: forward "
+                                   "('train' mode, batch-statistics BatchNorm), loss_rpn + loss_mos + loss_motion, backward, gradient all-reduce, Adam",
+                       "parallelism": ("one sample per GPU per step, weights replicated, ONE in-place NCCL all-reduce of the %.1f MB flat gradient "
+                                       "buffer per step, fused Adam on the flat buffers" % (ts.flat.numel * 4 / 1e6)) if world > 1 else "single GPU",
+                       "arithmetic": "fp32; sparse-conv forward and data gradient on tensor cores as 3xTF32, weight gradient fp32 FFMA; dense BEV convs cuDNN fp32 (TF32 off)",
+                       "parameters": int(ts.flat.numel), "points_per_step": int(batches[0][0].shape[0]),
+                       "l2": "no explicit flush: every step streams > 126 MB and inputs rotate over %d distinct clouds" % n_clouds},
+            "losses_first_last": [losses[0], last], "step_wall_ms": walls,
+            "gpu_launches": int(launches), "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "kernel": "insmos_sparse_conv_wgrad", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "definition": "algorithmic bytes of the weight-gradient launches of one step (SURVEY 8d formula per layer) / their CUDA-event time",
+                         "gflop": round(wg["flops"] / 1e9, 2), "ms_per_step": round(wg["ms"], 4)},
+            "kernels": kernels, "profiled_step_ms": round(prof_ms, 3),
+        }
+        out_stream.write(json.dumps(line) + "\n")
+        out_stream.flush()
+    if dist:
+        dist.destroy_process_group()
+
+
 def _claim_stdout():
     """stdout carries exactly ONE JSON line: everything else any library writes to fd 1 (NCCL's version banner, torchrun
     notices) is sent to stderr; returns the stream that still points at the real stdout."""
@@ -229,7 +334,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "train"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--min-timed-s", type=float, default=MIN_TIMED_S)
     ap.add_argument("--streams", type=int, default=2, help="forwards in flight on separate CUDA streams / host threads (0: the calling thread only)")
@@ -249,6 +354,9 @@ def main():
     torch.backends.cudnn.allow_tf32 = False
     if args.workload == "c4":
         run_c4(args, device, out_stream)
+        return
+    if args.workload == "train":
+        run_train(args, device, rank, local_rank, world, out_stream)
         return
     # every distinct input cloud is seen once before the timed region (first-touch sizes hit cudaMalloc in the caching
     # allocator: measured 9.4 -> 11.4 ms/step when the 4th cloud first appeared inside the timed loop)

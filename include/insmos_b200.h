@@ -409,13 +409,23 @@ int insmos_sparse_conv_wgrad(const float* in, int64_t n_in, int32_t Cin, const f
 
 /* column reductions over [n,C] fp32 matrices into fp64 sums (train-mode MinkowskiBatchNorm / nn.BatchNorm1d,
  * minkunet.py:52-131, spconv_unet.py:118):  mode 0: out0 = sum a;  mode 1: out0 = sum (a - mean)^2;
- * mode 2: g = (gate == NULL || gate > 0) ? a : 0, out0 = sum g, out1 = sum g * (b - mean) * invstd.   C <= 1024. */
+ * mode 2: g = (gate == NULL || gate > 0) ? a : 0, out0 = sum g, out1 = sum g * (b - mean) * invstd;
+ * mode 3: out0 = sum a, out1 = sum a^2 (one pass, exact products in fp64).   C <= 1024. */
 int insmos_column_moments(const float* a, const float* b, const float* gate, const float* mean, const float* invstd,
                           int64_t n, int32_t C, int32_t mode, double* out0, double* out1, void* stream);
 
-/* BatchNorm backward, elementwise part: dx = coef * (g - m0 - xhat * m1), g = dy gated by gate > 0 (fused ReLU) */
+/* per-channel constants of train-mode BatchNorm from the fp64 sums of insmos_column_moments(mode 3): mean, invstd, the fused
+ * affine (scale = gamma*invstd, shift = beta - mean*scale) for insmos_affine_act, and nn.BatchNorm1d's running-statistics
+ * update (running = (1-momentum)*running + momentum*batch, variance unbiased); running_* may be NULL. */
+int insmos_bn_train_finalize(const double* sum, const double* sumsq, int64_t n, int32_t C, const float* gamma, const float* beta,
+                             float eps, float momentum, float* mean, float* invstd, float* scale, float* shift,
+                             float* running_mean, float* running_var, void* stream);
+
+/* BatchNorm backward, elementwise part: dx = gamma*invstd*(g - s0/n - xhat*s1/n), g = dy gated by gate > 0 (fused ReLU), s0/s1 =
+ * the fp64 sums of insmos_column_moments(mode 2); also writes dbeta = s0, dgamma = s1 (either may be NULL). */
 int insmos_bn_bwd_apply(const float* dy, const float* x, const float* gate, const float* mean, const float* invstd,
-                        const float* coef, const float* m0, const float* m1, int64_t n, int32_t C, float* dx, void* stream);
+                        const float* gamma, const double* s0, const double* s1, int64_t n, int32_t C, float* dx,
+                        float* dgamma, float* dbeta, void* stream);
 
 /* out[idx[i],0:C] += src[i,0:C] (idx < 0 skipped; src row stride ldsrc): backward of insmos_gather_rows /
  * insmos_build_current_points / gather_features_by_pc_voxel_id.  out must be initialised by the caller. */

@@ -101,7 +101,8 @@ PROTOTYPES = {
     "insmos_sparse_conv_wgrad_slices": (_I32, [_I64, _I32, _I32, _I32]),
     "insmos_sparse_conv_wgrad": (C.c_int, [_P, _I64, _I32, _P, _I64, _I32, _P, _P, _I32, _I32, _P, _I32, _P, _P]),
     "insmos_column_moments": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P]),
-    "insmos_bn_bwd_apply": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P]),
+    "insmos_bn_train_finalize": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "insmos_bn_bwd_apply": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P]),
     "insmos_scatter_add_rows": (C.c_int, [_P, _I32, _I32, _P, _I64, _P, _P]),
     "insmos_center_targets": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, C.c_double, C.c_double, _I32, _F, _F, _I32, _F, _I32,
                                         _P, _P, _P, _P, _P]),
@@ -154,7 +155,7 @@ KERNELS_PER_CALL = {
     "insmos_xblock_build": 2, "insmos_leafgrid_build": 1, "insmos_rulebook_build_lg": 1, "insmos_rulebook_build_xb": 1, "insmos_rulebook_build_up": 1,
     "insmos_sparse_conv_fwd_umma": 1, "insmos_conv2d_nhwc_umma": 1, "insmos_conv2d_nhwc_tcgen05": 1,
     "insmos_conv_prep_weights_umma": 1, "insmos_bev_prep_weights_tcgen05": 1, "insmos_dense_scatter_nhwc": 1,
-    "insmos_sparse_conv_wgrad": 2, "insmos_column_moments": 1, "insmos_bn_bwd_apply": 1, "insmos_scatter_add_rows": 1,
+    "insmos_sparse_conv_wgrad": 2, "insmos_column_moments": 1, "insmos_bn_train_finalize": 1, "insmos_bn_bwd_apply": 1, "insmos_scatter_add_rows": 1,
     "insmos_center_targets": 1, "insmos_adam_step": 1,
 }
 PROFILE = None        # list collecting (name, start_event, end_event, meta) when profiling is on

@@ -95,49 +95,48 @@ def linear(x, weight, bias=None):
 
 
 class _BatchNormTrain(torch.autograd.Function):
-    """train-mode BatchNorm over [n, C] rows with an optional fused ReLU: batch mean, biased batch variance (two passes,
-    fp64 column sums), y = (x - mean) * invstd * gamma + beta.  Returns (y, mean, unbiased variance) -- the module updates
-    its running statistics from the last two exactly like nn.BatchNorm1d."""
+    """train-mode BatchNorm over [n, C] rows with an optional fused ReLU, three launches: column sums (sum x, sum x^2 in fp64,
+    one pass), per-channel constants + running-statistics update (insmos_bn_train_finalize), y = x*scale + shift (+ReLU).
+    Backward, two launches: (sum g, sum g*xhat) with the ReLU gate applied on the fly, then dx / dgamma / dbeta."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps, relu):
+    def forward(ctx, x, gamma, beta, eps, relu, momentum, running_mean, running_var):
         x = x.contiguous()
         n = x.shape[0]
-        mean = (ops.column_moments(x, 0) / n).float()
-        ssq = ops.column_moments(x, 1, mean=mean)
-        var = ssq / n
-        invstd = torch.rsqrt(var + eps).float()
-        scale = (gamma * invstd).contiguous()
-        shift = (beta - mean * scale).contiguous()
-        y = ops.affine_act(x, scale=scale, shift=shift, relu=relu)
-        ctx.save_for_backward(x, y if relu else None, mean, invstd, gamma)
-        ctx.relu = relu
-        unbiased = (ssq / max(n - 1, 1)).float()
-        ctx.mark_non_differentiable(mean, unbiased)
-        return y, mean, unbiased
+        s, ss = ops.column_moments(x, 3)
+        consts = ops.bn_train_finalize(s, ss, n, None if gamma is None else gamma.detach(), None if beta is None else beta.detach(), eps,
+                                       momentum, running_mean, running_var)
+        y = ops.affine_act(x, scale=consts[2], shift=consts[3], relu=relu)
+        ctx.save_for_backward(x, y if relu else None, consts, gamma)
+        return y
 
     @staticmethod
-    def backward(ctx, dy, _dmean, _dvar):
-        x, y, mean, invstd, gamma = ctx.saved_tensors
+    def backward(ctx, dy):
+        x, y, consts, gamma = ctx.saved_tensors
         dy = dy.contiguous()
-        n = x.shape[0]
-        s0, s1 = ops.column_moments(dy, 2, b=x, gate=y, mean=mean, invstd=invstd)
-        dbeta = s0.float()
-        dgamma = s1.float()
-        coef = (gamma * invstd).contiguous()
-        dx = ops.bn_bwd_apply(dy, x, y, mean, invstd, coef, (s0 / n).float().contiguous(), (s1 / n).float().contiguous())
-        return dx, dgamma, dbeta, None, None
+        s0, s1 = ops.column_moments(dy, 2, b=x, gate=y, mean=consts[0], invstd=consts[1])
+        dx, dgamma, dbeta = ops.bn_bwd_apply(dy, x, y, consts[0], consts[1], None if gamma is None else gamma.detach(), s0, s1)
+        if gamma is None:
+            dgamma = dbeta = None
+        return dx, dgamma, dbeta, None, None, None, None, None
 
 
 def batch_norm_train(bn, x, relu=False):
     """nn.BatchNorm1d `bn` in training mode applied to x [n, C] (+ ReLU) on the library's kernels; updates running stats."""
-    y, mean, unbiased = _BatchNormTrain.apply(x, bn.weight, bn.bias, bn.eps, relu)
-    if bn.track_running_stats:
+    if x.shape[0] < 2:
+        raise ValueError("batch_norm_train: more than one row per channel required (as nn.BatchNorm1d in training mode)")
+    track = bn.track_running_stats and bn.running_mean is not None
+    if track and bn.momentum is None:
+        raise NotImplementedError("cumulative-average BatchNorm (momentum=None) is not on the InsMOS path")
+    y = _BatchNormTrain.apply(x, bn.weight, bn.bias, bn.eps, relu, bn.momentum if track else 0.0,
+                              bn.running_mean if track else None, bn.running_var if track else None)
+    if track:
         with torch.no_grad():
             bn.num_batches_tracked += 1
-            m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-            bn.running_mean.mul_(1 - m).add_(mean, alpha=m)
-            bn.running_var.mul_(1 - m).add_(unbiased, alpha=m)
+        # the finalize kernel wrote the running statistics in place: bump their version counters (the folded eval-mode
+        # constants are cached on them)
+        torch.autograd.graph.increment_version(bn.running_mean)
+        torch.autograd.graph.increment_version(bn.running_var)
     return y
 
 

@@ -18,7 +18,7 @@
 // scheduling.
 #define WG_CIB 16
 #define WG_WARPS 8
-template <int M>
+template <int M, int U>
 __global__ void __launch_bounds__(WG_WARPS * 32)
 k_spconv_wgrad(const float* __restrict__ x, const float* __restrict__ dy, const uint16_t* __restrict__ seg,
                const uint32_t* __restrict__ entries, int TM, int K, int Cin, int Cout, int CoutP, int64_t n_tiles, int S,
@@ -32,35 +32,42 @@ k_spconv_wgrad(const float* __restrict__ x, const float* __restrict__ dy, const 
     for (int a = 0; a < WG_CIB; ++a)
 #pragma unroll
         for (int m = 0; m < M; ++m) acc[a][m] = 0.0f;
-    const bool vec = (Cin & 3) == 0;                                   // rows of x are 16-byte aligned multiples
+    const bool vec = (Cin & 3) == 0 && ci0 + WG_CIB <= Cin;            // rows of x are 16-byte aligned multiples
     for (int64_t tile = s + (int64_t)S * warp; tile < n_tiles; tile += (int64_t)S * WG_WARPS) {
         const uint16_t* tseg = seg + tile * (K + 1);
         const int start = tseg[k], n = (int)tseg[k + 1] - start;
         const uint32_t* tent = entries + tile * (int64_t)TM * K + start;
-        for (int p0 = 0; p0 < n; p0 += G) {
-            const int p = p0 + g;
-            if (p >= n) continue;
-            const uint32_t e = __ldg(tent + p);
-            const int64_t i = e & INSMOS_ROW_MASK, o = tile * TM + (e >> INSMOS_ROW_BITS);
-            float d[M];
+        // U pairs per lane in flight: first the U rule-book entries, then all their row loads, then the FFMAs -- the two
+        // dependent global-load latencies (entry -> rows) are paid once per U pairs instead of once per pair
+        for (int p0 = 0; p0 < n; p0 += G * U) {
+            uint32_t e[U];
 #pragma unroll
-            for (int m = 0; m < M; ++m) { const int co = c0 + 32 * m; d[m] = co < Cout ? __ldg(dy + o * Cout + co) : 0.0f; }
-            const float* xr = x + i * Cin + ci0;
-            float xv[WG_CIB];
-            if (vec && ci0 + WG_CIB <= Cin) {
+            for (int u = 0; u < U; ++u) { const int p = p0 + g + G * u; e[u] = p < n ? __ldg(tent + p) : 0xffffffffu; }
+            float d[U][M], xv[U][WG_CIB];
 #pragma unroll
-                for (int q = 0; q < WG_CIB / 4; ++q) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(xr) + q);
-                    xv[4 * q] = v.x; xv[4 * q + 1] = v.y; xv[4 * q + 2] = v.z; xv[4 * q + 3] = v.w;
+            for (int u = 0; u < U; ++u) {
+                const bool ok = e[u] != 0xffffffffu;
+                const int64_t i = ok ? (int64_t)(e[u] & INSMOS_ROW_MASK) : 0, o = ok ? tile * TM + (e[u] >> INSMOS_ROW_BITS) : 0;
+#pragma unroll
+                for (int m = 0; m < M; ++m) { const int co = c0 + 32 * m; d[u][m] = (ok && co < Cout) ? __ldg(dy + o * Cout + co) : 0.0f; }
+                const float* xr = x + i * Cin + ci0;
+                if (vec) {
+#pragma unroll
+                    for (int q = 0; q < WG_CIB / 4; ++q) {
+                        const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(xr) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        xv[u][4 * q] = v.x; xv[u][4 * q + 1] = v.y; xv[u][4 * q + 2] = v.z; xv[u][4 * q + 3] = v.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int a = 0; a < WG_CIB; ++a) xv[u][a] = (ok && ci0 + a < Cin) ? __ldg(xr + a) : 0.0f;
                 }
-            } else {
-#pragma unroll
-                for (int a = 0; a < WG_CIB; ++a) xv[a] = ci0 + a < Cin ? __ldg(xr + a) : 0.0f;
             }
 #pragma unroll
-            for (int a = 0; a < WG_CIB; ++a)
+            for (int u = 0; u < U; ++u)                                 // fixed order: the sum does not depend on scheduling
 #pragma unroll
-                for (int m = 0; m < M; ++m) acc[a][m] = __fmaf_rn(xv[a], d[m], acc[a][m]);
+                for (int a = 0; a < WG_CIB; ++a)
+#pragma unroll
+                    for (int m = 0; m < M; ++m) acc[a][m] = __fmaf_rn(xv[u][a], d[u][m], acc[a][m]);
         }
     }
     // lane groups -> group 0 (fixed shuffle tree), then per 32-channel slab m: warps -> shared memory -> fixed-order sum
@@ -124,10 +131,10 @@ extern "C" int insmos_sparse_conv_wgrad(const float* in, int64_t n_in, int32_t C
     const int64_t n_tiles = ceil_div64(n_out, TM);
     const dim3 grid((unsigned)K, (unsigned)S, (unsigned)((Cin + WG_CIB - 1) / WG_CIB));
     switch (M) {
-        case 1: k_spconv_wgrad<1><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, CoutP, n_tiles, S, partial); break;
-        case 2: k_spconv_wgrad<2><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, CoutP, n_tiles, S, partial); break;
-        case 3: k_spconv_wgrad<3><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, CoutP, n_tiles, S, partial); break;
-        default: k_spconv_wgrad<4><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, CoutP, n_tiles, S, partial); break;
+        case 1: k_spconv_wgrad<1, 4><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, CoutP, n_tiles, S, partial); break;
+        case 2: k_spconv_wgrad<2, 4><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, CoutP, n_tiles, S, partial); break;
+        case 3: k_spconv_wgrad<3, 2><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, CoutP, n_tiles, S, partial); break;
+        default: k_spconv_wgrad<4, 2><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, CoutP, n_tiles, S, partial); break;
     }
     INSMOS_CHECK_LAUNCH("k_spconv_wgrad");
     k_wgrad_reduce<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(partial, S, n, dweight);
@@ -141,6 +148,8 @@ extern "C" int insmos_sparse_conv_wgrad(const float* in, int64_t n_in, int32_t C
 //   mode 0: out0[c] = sum_r a[r][c]
 //   mode 1: out0[c] = sum_r (a[r][c] - mean[c])^2
 //   mode 2: g = gate ? (gate[r][c] > 0 ? a : 0) : a;  out0[c] = sum_r g,  out1[c] = sum_r g * (b[r][c] - mean[c]) * invstd[c]
+//   mode 3: out0[c] = sum_r a[r][c],  out1[c] = sum_r a[r][c]^2   (one pass; both sums are exact products accumulated in fp64,
+//           so var = out1/n - mean^2 formed in fp64 loses nothing an fp32 two-pass variance would keep)
 // Block partials are accumulated in double; a block adds its column sums to the double outputs with atomicAdd (the order
 // of the ~600 block contributions varies, in double that is invisible after rounding to fp32).
 #define CM_THREADS 256
@@ -158,11 +167,12 @@ k_column_moments(const float* __restrict__ a, const float* __restrict__ b, const
         const int rl = C <= CM_THREADS ? threadIdx.x / C : 0;
         double s0 = 0.0, s1 = 0.0;
         if (c < C && rl < RL) {
-            const float mu = (mode != 0) ? mean[c] : 0.0f;
+            const float mu = (mode == 1 || mode == 2) ? mean[c] : 0.0f;
             const float is = (mode == 2) ? invstd[c] : 0.0f;
             for (int64_t r = r0 + rl; r < r1; r += RL) {
                 const float v = a[r * C + c];
                 if (mode == 0) s0 += (double)v;
+                else if (mode == 3) { s0 += (double)v; s1 += (double)v * (double)v; }
                 else if (mode == 1) { const float d = v - mu; s0 += (double)d * (double)d; }
                 else {
                     const float gv = (gate && !(gate[r * C + c] > 0.0f)) ? 0.0f : v;
@@ -177,7 +187,7 @@ k_column_moments(const float* __restrict__ a, const float* __restrict__ b, const
             double t0 = 0.0, t1 = 0.0;
             for (int q = 0; q < RL; ++q) { t0 += sh[q * CS + (c - cbase)]; t1 += sh[(RL + q) * CS + (c - cbase)]; }
             atomicAdd(out0 + c, t0);
-            if (mode == 2) atomicAdd(out1 + c, t1);
+            if (mode >= 2) atomicAdd(out1 + c, t1);
         }
         __syncthreads();
     }
@@ -185,12 +195,12 @@ k_column_moments(const float* __restrict__ a, const float* __restrict__ b, const
 
 extern "C" int insmos_column_moments(const float* a, const float* b, const float* gate, const float* mean, const float* invstd,
                                      int64_t n, int32_t C, int32_t mode, double* out0, double* out1, void* stream) {
-    if (!out0 || C <= 0 || C > 1024 || n < 0 || mode < 0 || mode > 2 || (n > 0 && !a) || (mode != 0 && !mean) ||
-        (mode == 2 && (!b || !invstd || !out1)))
+    if (!out0 || C <= 0 || C > 1024 || n < 0 || mode < 0 || mode > 3 || (n > 0 && !a) || ((mode == 1 || mode == 2) && !mean) ||
+        (mode == 2 && (!b || !invstd)) || (mode >= 2 && !out1))
         return INSMOS_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     INSMOS_CHECK_CUDA(cudaMemsetAsync(out0, 0, sizeof(double) * C, st));
-    if (mode == 2) INSMOS_CHECK_CUDA(cudaMemsetAsync(out1, 0, sizeof(double) * C, st));
+    if (mode >= 2) INSMOS_CHECK_CUDA(cudaMemsetAsync(out1, 0, sizeof(double) * C, st));
     if (n == 0) return INSMOS_OK;
     int64_t blocks = 148 * 4;
     int64_t rpb = ceil_div64(n, blocks);
@@ -204,28 +214,66 @@ extern "C" int insmos_column_moments(const float* a, const float* b, const float
     return INSMOS_OK;
 }
 
-// train-mode BatchNorm backward, elementwise part:  dx = coef[c] * (g - m0[c] - xhat * m1[c])  with g = dy gated by the ReLU
-// (gate > 0), xhat = (x - mean) * invstd, coef = gamma * invstd, m0 = sum(g)/n, m1 = sum(g * xhat)/n.
+// train-mode BatchNorm, per-channel constants from the fp64 column sums of insmos_column_moments(mode 3): batch mean, biased
+// variance -> invstd, the fused affine (scale, shift) for insmos_affine_act, and the running-statistics update of
+// nn.BatchNorm1d (momentum m: running = (1 - m) * running + m * batch, the variance unbiased by n / (n - 1)).
+__global__ void k_bn_train_finalize(const double* __restrict__ sum, const double* __restrict__ sumsq, double n, int C,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                                    float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ scale,
+                                    float* __restrict__ shift, float* __restrict__ running_mean, float* __restrict__ running_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double mu = sum[c] / n;
+    double var = sumsq[c] / n - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float muf = (float)mu;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = (gamma ? gamma[c] : 1.0f) * is;
+    mean[c] = muf; invstd[c] = is; scale[c] = sc;
+    shift[c] = (beta ? beta[c] : 0.0f) - muf * sc;
+    if (running_mean) running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * muf;
+    if (running_var) running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)(var * (n / (n > 1.0 ? n - 1.0 : 1.0)));
+}
+
+extern "C" int insmos_bn_train_finalize(const double* sum, const double* sumsq, int64_t n, int32_t C, const float* gamma,
+                                        const float* beta, float eps, float momentum, float* mean, float* invstd, float* scale,
+                                        float* shift, float* running_mean, float* running_var, void* stream) {
+    if (!sum || !sumsq || n <= 0 || C <= 0 || !mean || !invstd || !scale || !shift) return INSMOS_ERR_INVALID_ARG;
+    k_bn_train_finalize<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sumsq, (double)n, C, gamma, beta, eps, momentum, mean, invstd,
+                                                                           scale, shift, running_mean, running_var);
+    INSMOS_CHECK_LAUNCH("k_bn_train_finalize");
+    return INSMOS_OK;
+}
+
+// train-mode BatchNorm backward, elementwise part:  dx = gamma * invstd * (g - s0/n - xhat * s1/n)  with g = dy gated by the
+// fused ReLU (gate > 0), xhat = (x - mean) * invstd, s0 = sum(g), s1 = sum(g * xhat) (fp64, insmos_column_moments mode 2).
+// The first C threads also write dbeta = s0 and dgamma = s1.
 __global__ void k_bn_bwd_apply(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gate,
-                               const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ coef,
-                               const float* __restrict__ m0, const float* __restrict__ m1, int64_t total, int C,
-                               float* __restrict__ dx) {
+                               const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                               const double* __restrict__ s0, const double* __restrict__ s1, double inv_n, int64_t total, int C,
+                               float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < C) {
+        if (dbeta) dbeta[i] = (float)s0[i];
+        if (dgamma) dgamma[i] = (float)s1[i];
+    }
     if (i >= total) return;
     const int c = (int)(i % C);
     float g = dy[i];
     if (gate && !(gate[i] > 0.0f)) g = 0.0f;
-    const float xhat = (x[i] - mean[c]) * invstd[c];
-    dx[i] = coef[c] * (g - m0[c] - xhat * m1[c]);
+    const float is = invstd[c];
+    const float xhat = (x[i] - mean[c]) * is;
+    const float m0 = (float)(s0[c] * inv_n), m1 = (float)(s1[c] * inv_n);
+    dx[i] = (gamma ? gamma[c] : 1.0f) * is * (g - m0 - xhat * m1);
 }
 
 extern "C" int insmos_bn_bwd_apply(const float* dy, const float* x, const float* gate, const float* mean, const float* invstd,
-                                   const float* coef, const float* m0, const float* m1, int64_t n, int32_t C, float* dx,
-                                   void* stream) {
-    if (C <= 0 || n < 0 || (n > 0 && (!dy || !x || !dx)) || !mean || !invstd || !coef || !m0 || !m1) return INSMOS_ERR_INVALID_ARG;
-    if (n == 0) return INSMOS_OK;
+                                   const float* gamma, const double* s0, const double* s1, int64_t n, int32_t C, float* dx,
+                                   float* dgamma, float* dbeta, void* stream) {
+    if (C <= 0 || n <= 0 || !dy || !x || !dx || !mean || !invstd || !s0 || !s1) return INSMOS_ERR_INVALID_ARG;
     const int64_t total = n * C;
-    k_bn_bwd_apply<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(dy, x, gate, mean, invstd, coef, m0, m1, total, C, dx);
+    k_bn_bwd_apply<<<(unsigned)ceil_div64(total > C ? total : C, 256), 256, 0, (cudaStream_t)stream>>>(
+        dy, x, gate, mean, invstd, gamma, s0, s1, 1.0 / (double)n, total, C, dx, dgamma, dbeta);
     INSMOS_CHECK_LAUNCH("k_bn_bwd_apply");
     return INSMOS_OK;
 }

@@ -844,21 +844,34 @@ def scatter_add_rows(src, idx, n_rows):
 
 
 def column_moments(a, mode, b=None, gate=None, mean=None, invstd=None):
-    """fp64 column sums over [n,C]: mode 0 sum(a); 1 sum((a-mean)^2); 2 (sum(g), sum(g*(b-mean)*invstd)), g = a gated by gate>0."""
+    """fp64 column sums over [n,C]: mode 0 sum(a); 1 sum((a-mean)^2); 2 (sum(g), sum(g*(b-mean)*invstd)), g = a gated by gate>0;
+    3 (sum(a), sum(a^2))."""
     a = _req(a, F32, "column_moments")
     n, Cc = a.shape
-    out0 = torch.empty(Cc, dtype=torch.float64, device=a.device)
-    out1 = torch.empty(Cc, dtype=torch.float64, device=a.device) if mode == 2 else None
-    call("insmos_column_moments", _p(a), _p(b), _p(gate), _p(mean), _p(invstd), n, Cc, int(mode), _p(out0), _p(out1), _stream())
-    return out0 if mode != 2 else (out0, out1)
+    out = torch.empty((2, Cc), dtype=torch.float64, device=a.device)
+    call("insmos_column_moments", _p(a), _p(b), _p(gate), _p(mean), _p(invstd), n, Cc, int(mode), _p(out[0]), _p(out[1]) if mode >= 2 else None,
+         _stream())
+    return out[0] if mode < 2 else (out[0], out[1])
 
 
-def bn_bwd_apply(dy, x, gate, mean, invstd, coef, m0, m1):
+def bn_train_finalize(s, ss, n, gamma, beta, eps, momentum, running_mean=None, running_var=None):
+    """-> consts [4, C] f32: rows mean, invstd, scale, shift; updates the running statistics in place."""
+    Cc = s.shape[0]
+    consts = torch.empty((4, Cc), dtype=F32, device=s.device)
+    call("insmos_bn_train_finalize", _p(s), _p(ss), int(n), Cc, _p(gamma), _p(beta), float(eps), float(momentum), _p(consts[0]), _p(consts[1]),
+         _p(consts[2]), _p(consts[3]), _p(running_mean), _p(running_var), _stream())
+    return consts
+
+
+def bn_bwd_apply(dy, x, gate, mean, invstd, gamma, s0, s1):
+    """-> (dx [n,C], dgamma [C], dbeta [C])"""
     dy = _req(dy, F32, "bn_bwd_apply")
     n, Cc = dy.shape
     dx = torch.empty_like(dy)
-    call("insmos_bn_bwd_apply", _p(dy), _p(x), _p(gate), _p(mean), _p(invstd), _p(coef), _p(m0), _p(m1), n, Cc, _p(dx), _stream())
-    return dx
+    dgb = torch.empty((2, Cc), dtype=F32, device=dy.device)
+    call("insmos_bn_bwd_apply", _p(dy), _p(x), _p(gate), _p(mean), _p(invstd), _p(gamma), _p(s0), _p(s1), n, Cc, _p(dx), _p(dgb[0]), _p(dgb[1]),
+         _stream())
+    return dx, dgb[0], dgb[1]
 
 
 def center_targets(gt_boxes, max_objs, H, W, ncls, x_min, y_min, vx, vy, out_size_factor, min_overlap, min_radius, range_is_fp64=False):

@@ -29,8 +29,10 @@ class FlatParameters:
         if not self.params:
             raise ValueError("no trainable parameters")
         dev = self.params[0].device
-        if dev.type != "cuda" or any(p.dtype != torch.float32 or p.device != dev for p in self.params):
-            raise RuntimeError("FlatParameters: float32 CUDA parameters on one device required (no CPU path)")
+        if any(p.dtype != torch.float32 or p.device != dev for p in self.params):
+            raise RuntimeError("FlatParameters: float32 parameters on one device required")
+        # (the buffers themselves are device-agnostic host logic -- the gloo tests exercise the exchange on CPU tensors;
+        # the optimizer kernel and the model are CUDA-only and refuse anything else)
         n = sum(p.numel() for p in self.params)
         self.data = torch.empty(n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
