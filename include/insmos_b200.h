@@ -95,6 +95,10 @@ typedef struct {
     const float* bias;      /* [dev] [Cout] or NULL */
     const float* residual;  /* [dev] [N_out, Cout] or NULL */
     int32_t relu;
+    /* [dev] one int32 or NULL.  Dead-row elimination: output rows below *first_row are not needed by
+     * the caller and MAY be left unwritten (kernels that do not implement the hint compute every row).  The value lives on the
+     * device (insmos_time_row_starts), so no host read sits between the coordinate ops and the convolutions. */
+    const int32_t* first_row;
 } insmos_epilogue_t;
 
 const char* insmos_version(void);
@@ -389,6 +393,23 @@ int insmos_instance_stats(const int32_t* ids, int32_t ncls, int32_t col, int64_t
  * new_label is i32 [nb+1] (entry 0 unused). */
 int insmos_relabel_instances(const int32_t* ids, int32_t ncls, int32_t col, int64_t n, const int32_t* new_label,
                              int32_t nb, int32_t* labels, void* stream);
+
+/* ---- dead-row elimination for the 4D MotionNet decoder ----------------------------------------------
+ * Only the rows of the newest scan (time index 0) leave MotionNet (motionnet.py:42-45); a 3x3x3x3 convolution reaches one
+ * time index back, so the last decoder layers need only the rows with time index >= -j.
+ * starts[j] (j = 0..15) = smallest row index whose time coordinate (column tcol of coords [n,ncol]) is >= -j, or n when there
+ * is none: every row needed at threshold -j has an index >= starts[j] whatever the input order (time-ordered input, as
+ * predict_mos.py:146-158 produces it, makes the needed rows exactly a suffix).  starts must hold 33 int32 (16 results + scratch). */
+int insmos_time_row_starts(const int32_t* coords, int64_t n, int32_t ncol, int32_t tcol, int32_t* starts, void* stream);
+
+/* insmos_rulebook_build_lg restricted to the output tiles that contain rows >= *first_row ([dev], may be NULL = all);
+ * seg / entries of the skipped tiles are left unwritten and pair_count counts the built tiles only. */
+int insmos_rulebook_build_lg_from(const int32_t* out_coords, int64_t n_out,
+                                  const insmos_slot_t* in_table, int64_t in_cap,
+                                  const void* grid, int64_t grid_cap, const int32_t* step,
+                                  const insmos_mapspec_t* spec, int32_t TM,
+                                  uint16_t* seg, uint32_t* entries, unsigned long long* pair_count,
+                                  const int32_t* first_row, void* stream);
 
 /* ---- training step (BASELINE config 5) -----------------------------------------------
  * The reference trains through autograd over MinkowskiEngine / spconv (models/models.py:61-98,330-347,

@@ -24,7 +24,7 @@ class MapSpec(C.Structure):
 
 class Epilogue(C.Structure):
     _fields_ = [("scale", C.c_void_p), ("shift", C.c_void_p), ("bias", C.c_void_p), ("residual", C.c_void_p),
-                ("relu", C.c_int32)]
+                ("relu", C.c_int32), ("first_row", C.c_void_p)]
 
 
 _P = C.c_void_p
@@ -97,6 +97,8 @@ PROTOTYPES = {
     "insmos_nms_rotated_pairs": (C.c_int, [_P, _I32, _F, _I32, _P, _P, _I64, _P, _P, _P, _P]),
     "insmos_boxes_to_voxel_units": (C.c_int, [_P, _P, _I32, C.POINTER(_F), C.POINTER(_F), _F, _P, _P]),
     "insmos_box_membership": (C.c_int, [_P, _I64, _P, _I32, _F, _P, _I32, _P, _P]),
+    "insmos_time_row_starts": (C.c_int, [_P, _I64, _I32, _I32, _P, _P]),
+    "insmos_rulebook_build_lg_from": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, C.POINTER(_I32), C.POINTER(MapSpec), _I32, _P, _P, _P, _P, _P]),
     # training step (N3)
     "insmos_sparse_conv_wgrad_slices": (_I32, [_I64, _I32, _I32, _I32]),
     "insmos_sparse_conv_wgrad": (C.c_int, [_P, _I64, _I32, _P, _I64, _I32, _P, _P, _I32, _I32, _P, _I32, _P, _P]),
@@ -127,7 +129,12 @@ def load():
         raise RuntimeError(
             "insmos_b200: %s is missing. Build it with `python -m insmos_b200.build` "
             "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+    # PyDLL: the GIL is HELD across a C-ABI call.  Every entry point only queues kernels (a few microseconds, never a device
+    # synchronisation), and with two forwards in flight on two host threads a CDLL call -- which drops and re-takes the GIL --
+    # hands the interpreter to the other thread ~280 times per step; each hand-off costs a condition-variable wake-up.  The
+    # threads now switch where they should: at the blocking device->host reads of data-dependent sizes (torch releases the
+    # GIL there).  INSMOS_HOLD_GIL=0 restores CDLL for A/B measurements.
+    lib = (C.PyDLL if os.environ.get("INSMOS_HOLD_GIL", "1") != "0" else C.CDLL)(LIB_PATH)
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)          # AttributeError if the library does not export the symbol
         fn.restype = res
@@ -155,7 +162,7 @@ KERNELS_PER_CALL = {
     "insmos_xblock_build": 2, "insmos_leafgrid_build": 1, "insmos_rulebook_build_lg": 1, "insmos_rulebook_build_xb": 1, "insmos_rulebook_build_up": 1,
     "insmos_sparse_conv_fwd_umma": 1, "insmos_conv2d_nhwc_umma": 1, "insmos_conv2d_nhwc_tcgen05": 1,
     "insmos_conv_prep_weights_umma": 1, "insmos_bev_prep_weights_tcgen05": 1, "insmos_dense_scatter_nhwc": 1,
-    "insmos_sparse_conv_wgrad": 2, "insmos_column_moments": 1, "insmos_bn_train_finalize": 1, "insmos_bn_bwd_apply": 1, "insmos_scatter_add_rows": 1,
+    "insmos_time_row_starts": 2, "insmos_rulebook_build_lg_from": 1, "insmos_sparse_conv_wgrad": 2, "insmos_column_moments": 1, "insmos_bn_train_finalize": 1, "insmos_bn_bwd_apply": 1, "insmos_scatter_add_rows": 1,
     "insmos_center_targets": 1, "insmos_adam_step": 1,
 }
 PROFILE = None        # list collecting (name, start_event, end_event, meta) when profiling is on

@@ -52,8 +52,10 @@ class CoordinateManager:
             self.parents[(key, new_key)] = parent
         return new_key
 
-    def rulebook(self, kind, in_key, out_key, ksize, stride):
-        k = (kind, in_key, out_key, ksize, stride)
+    def rulebook(self, kind, in_key, out_key, ksize, stride, first_row=None):
+        """first_row (device int32, optional): the caller only needs output rows >= *first_row; such a book is cached
+        apart from the full one and only handed to callers that ask for it (dead-row elimination)"""
+        k = (kind, in_key, out_key, ksize, stride) if first_row is None else (kind, in_key, out_key, ksize, stride, "rows_from")
         rb = self.rulebooks.get(k)
         if rb is None:
             if kind == "conv":
@@ -64,7 +66,8 @@ class CoordinateManager:
             parent = self.parents.get((out_key, in_key)) if kind == "up" else None
             # every set of this manager holds coordinates that are multiples of its tensor stride -> x-block probing
             rb = ops.build_rulebook(self.sets[out_key], self.sets[in_key], spec, parent=parent,
-                                    xstep=in_key[0] if kind == "conv" else None, step=in_key if kind == "conv" else None)
+                                    xstep=in_key[0] if kind == "conv" else None, step=in_key if kind == "conv" else None,
+                                    first_row=first_row if kind == "conv" else None)
             self.rulebooks[k] = rb
         return rb
 
@@ -272,18 +275,20 @@ class _ConvBase(nn.Module):
         f = _ag.sparse_conv(x.F, w, rb, rb_t, flip)
         return x._like(f if self.bias is None else f + self.bias, out_key)
 
-    def forward(self, x, bn=None, relu=False, residual=None, algo=0):
+    def forward(self, x, bn=None, relu=False, residual=None, algo=0, first_row=None, rb_first_row=None):
+        """first_row / rb_first_row (device int32 tensors, inference only): output rows below *first_row are not needed by the
+        caller; rb_first_row is the smallest such bound over every layer that shares this layer's kernel map."""
         if bn is None and not relu and residual is None and _ag.needs_grad(x.F, self.kernel, self.bias):
             return self._forward_train(x)
         scale, shift = _fold(bn)
         bias = None if self.bias is None else self.bias.view(-1)
         mgr, in_key = x.coordinate_manager, x.coordinate_map_key
         if self.kernel_volume == 1 and all(s == 1 for s in self.stride):
-            f = ops.linear(x.F, self.kernel, scale=scale, shift=shift, bias=bias, residual=residual, relu=relu)
+            f = ops.linear(x.F, self.kernel, scale=scale, shift=shift, bias=bias, residual=residual, relu=relu, first_row=first_row)
             return x._like(f)
         if not self.transposed:
             out_key = in_key if all(s == 1 for s in self.stride) else mgr.stride(in_key, self.stride)
-            rb = mgr.rulebook("conv", in_key, out_key, self.kernel_size, self.stride)
+            rb = mgr.rulebook("conv", in_key, out_key, self.kernel_size, self.stride, first_row=rb_first_row)
         else:
             out_key = tuple(k // s for k, s in zip(in_key, self.stride))
             if out_key not in mgr.sets:
@@ -293,7 +298,8 @@ class _ConvBase(nn.Module):
                 raise NotImplementedError("transposed convolution with kernel != stride is not on the InsMOS path")
             rb = mgr.rulebook("up", in_key, out_key, self.kernel_size, self.stride)
         w = self.kernel if self.kernel.dim() == 3 else self.kernel.view(1, *self.kernel.shape)
-        f = ops.sparse_conv(x.F, w, rb, scale=scale, shift=shift, bias=bias, residual=residual, relu=relu, algo=algo)
+        f = ops.sparse_conv(x.F, w, rb, scale=scale, shift=shift, bias=bias, residual=residual, relu=relu, algo=algo,
+                            first_row=first_row)
         return x._like(f, out_key)
 
     def extra_repr(self):

@@ -24,21 +24,24 @@ class BasicBlock(nn.Module):
         self.relu = ME.MinkowskiReLU(inplace=True)
         self.downsample = downsample
 
-    def forward(self, x):
+    def forward(self, x, rows=None):
+        """rows (inference only): (first_row of conv1, first_row of conv2 / downsample / output, bound for a kernel map that only
+        this block uses or None) -- device int32 tensors, dead-row elimination"""
         if self.training:
             out = self.norm1(self.conv1(x), relu=True)
             out = self.norm2(self.conv2(out))
             res = x if self.downsample is None else self.downsample(x)
             return self.relu(out._like(out.F + res.F))
-        out = self.conv1(x, bn=self.norm1, relu=True)
+        r1, r2, rbr = rows if rows is not None else (None, None, None)
+        out = self.conv1(x, bn=self.norm1, relu=True, first_row=r1, rb_first_row=rbr)
         if self.downsample is None:
             res = x
         elif isinstance(self.downsample, nn.Sequential) and len(self.downsample) == 2 and \
                 isinstance(self.downsample[1], ME.MinkowskiBatchNorm):
-            res = self.downsample[0](x, bn=self.downsample[1])
+            res = self.downsample[0](x, bn=self.downsample[1], first_row=r2)
         else:
             res = self.downsample(x)
-        return self.conv2(out, bn=self.norm2, residual=res.F, relu=True)
+        return self.conv2(out, bn=self.norm2, residual=res.F, relu=True, first_row=r2, rb_first_row=rbr)
 
 
 class Bottleneck(nn.Module):

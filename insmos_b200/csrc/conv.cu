@@ -257,6 +257,8 @@ __global__ void __launch_bounds__(128)
 k_linear_row(const float* __restrict__ in, const float* __restrict__ W, float* __restrict__ out,
              int64_t n, int Cin, int Cout, insmos_epilogue_t ep) {
     extern __shared__ __align__(16) float sw[];                   // [Cin][COUTP] | scale[COUTP] | shift[COUTP] | bias[COUTP]
+    const int64_t first = ep.first_row ? (int64_t)__ldg(ep.first_row) : 0;          // rows below are not needed (dead-row hint)
+    if ((int64_t)(blockIdx.x + 1) * (128 * R) <= first) return;
     float* sc = sw + (size_t)Cin * COUTP;
     for (int i = threadIdx.x; i < Cin * COUTP; i += blockDim.x) {
         const int ci = i / COUTP, co = i - ci * COUTP;
@@ -273,7 +275,7 @@ k_linear_row(const float* __restrict__ in, const float* __restrict__ W, float* _
     bool ok[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        ok[r] = row0 + 128 * r < n;
+        ok[r] = row0 + 128 * r < n && row0 + 128 * r >= first;
         x[r] = reinterpret_cast<const float4*>(in + (ok[r] ? row0 + 128 * r : 0) * Cin);
     }
     float acc[R][COUTP];

@@ -59,8 +59,10 @@ k_spconv_tc4(TcArgs p) {
     const int unit = (int)blockIdx.x * (nwarps / wpt) + unit_local;
     const int tile = unit / p.groups;
     const int grp = unit - tile * p.groups;
-    const bool active = tile < (int)p.n_tiles;
     const int TM = p.TM, K = p.K;
+    // dead-row elimination: a tile whose rows all lie below *first_row is not needed by the caller
+    const bool active = tile < (int)p.n_tiles &&
+                        !(p.ep.first_row && (int64_t)(tile + 1) * TM <= (int64_t)__ldg(p.ep.first_row));
     const int nbk = (K + wpt - 1) / wpt;                             // buckets of this warp: k = sub, sub + wpt, ...
     const int cap = nbk * (1 + TM / 16);                             // chunk-list capacity per warp
     float* acc = sm + (size_t)warp * TM * CW;

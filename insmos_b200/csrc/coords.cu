@@ -354,3 +354,41 @@ extern "C" int insmos_voxelize3d(const float* points, int64_t n, int32_t C,
     INSMOS_CHECK_LAUNCH("k_v3d_reduce");
     return INSMOS_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Dead-row elimination for the 4D MotionNet decoder: starts[j] = smallest row index whose time
+// coordinate is >= -j (j = 0..15), n when there is none.  Class of a row = clamp(-t, 0, 16); per-block minima of the row
+// index per class in shared memory, one global atomicMin per class and block, then a 1-thread prefix minimum
+// (a row of class c serves every threshold j >= c).
+#define TRS_CLASSES 17
+__global__ void k_time_row_starts(const int32_t* __restrict__ coords, int64_t n, int ncol, int tcol, int32_t* __restrict__ cls_min) {
+    __shared__ int smin[TRS_CLASSES];
+    if (threadIdx.x < TRS_CLASSES) smin[threadIdx.x] = INT_MAX;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int t = coords[i * ncol + tcol];
+        const int c = t >= 0 ? 0 : (t < -16 ? 16 : -t);
+        atomicMin(&smin[c], (int)i);
+    }
+    __syncthreads();
+    if (threadIdx.x < TRS_CLASSES && smin[threadIdx.x] != INT_MAX) atomicMin(&cls_min[threadIdx.x], smin[threadIdx.x]);
+}
+__global__ void k_time_row_prefix(const int32_t* __restrict__ cls_min, int32_t n, int32_t* __restrict__ starts) {
+    int m = n;
+    for (int j = 0; j < 16; ++j) { m = min(m, cls_min[j]); starts[j] = m; }
+}
+
+extern "C" int insmos_time_row_starts(const int32_t* coords, int64_t n, int32_t ncol, int32_t tcol, int32_t* starts, void* stream) {
+    if (!starts || n < 0 || n > INT_MAX || ncol <= 0 || tcol < 0 || tcol >= ncol || (n > 0 && !coords)) return INSMOS_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t* cls_min = starts + 16;                                      // scratch: starts holds 16 + 17 ints
+    INSMOS_CHECK_CUDA(cudaMemsetAsync(cls_min, 0x7f, sizeof(int32_t) * TRS_CLASSES, st));       // 0x7f7f7f7f > any row index
+    if (n > 0) {
+        k_time_row_starts<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(coords, n, ncol, tcol, cls_min);
+        INSMOS_CHECK_LAUNCH("k_time_row_starts");
+    }
+    k_time_row_prefix<<<1, 1, 0, st>>>(cls_min, (int32_t)n, starts);
+    INSMOS_CHECK_LAUNCH("k_time_row_prefix");
+    return INSMOS_OK;
+}

@@ -202,8 +202,10 @@ k_rulebook_tiles(const int32_t* __restrict__ out_coords, int64_t n_out,
                  uint16_t* __restrict__ seg, uint32_t* __restrict__ entries,
                  unsigned long long* pair_count, const int32_t* __restrict__ parent,
                  const XBlockSlot* __restrict__ xtable, uint64_t xmask, int xstep,
-                 const unsigned long long* __restrict__ lgkeys, const int32_t* __restrict__ lgrows, uint64_t lgmask, LgGeom lg) {
+                 const unsigned long long* __restrict__ lgkeys, const int32_t* __restrict__ lgrows, uint64_t lgmask, LgGeom lg,
+                 const int32_t* __restrict__ first_row) {
     extern __shared__ __align__(16) int smem[];
+    if (first_row && (int64_t)(blockIdx.x + 1) * TM <= (int64_t)__ldg(first_row)) return;     // tile not needed (dead-row elimination)
     const int K = spec.K, ncol = spec.ncol, ndim = spec.ndim;
     int* nbr = smem;                                            // [TM*K] in-row or -1
     int64_t* delta = reinterpret_cast<int64_t*>(nbr + ((TM * K + 1) & ~1));   // [K] packed key delta of offset k
@@ -477,7 +479,8 @@ static int rulebook_build_impl(const int32_t* out_coords, int64_t n_out,
                                const insmos_mapspec_t* spec, int32_t TM,
                                uint16_t* seg, uint32_t* entries, unsigned long long* pair_count, void* stream,
                                const void* xtable = nullptr, int64_t xcap = 0, int32_t xstep = 0,
-                               const void* lgrid = nullptr, int64_t lgcap = 0, const int32_t* lgstep = nullptr) {
+                               const void* lgrid = nullptr, int64_t lgcap = 0, const int32_t* lgstep = nullptr,
+                               const int32_t* first_row = nullptr) {
     if (!out_coords || !spec || !seg || !entries || n_out < 0) return INSMOS_ERR_INVALID_ARG;
     if (parent) {
         if (spec->mode != 1) return INSMOS_ERR_INVALID_ARG;
@@ -535,7 +538,7 @@ static int rulebook_build_impl(const int32_t* out_coords, int64_t n_out,
     k_rulebook_tiles<<<(unsigned)n_tiles, RB_THREADS, smem, (cudaStream_t)stream>>>(
         out_coords, n_out, in_table, (uint64_t)(in_cap - 1), *spec, TM, seg, entries, pair_count, parent,
         reinterpret_cast<const XBlockSlot*>(xtable), (uint64_t)(xcap > 0 ? xcap - 1 : 0), xstep,
-        lgkeys, lgrows, (uint64_t)(lgcap > 0 ? lgcap - 1 : 0), lg);
+        lgkeys, lgrows, (uint64_t)(lgcap > 0 ? lgcap - 1 : 0), lg, first_row);
     INSMOS_CHECK_LAUNCH("k_rulebook_tiles");
     return INSMOS_OK;
 }
@@ -649,4 +652,16 @@ extern "C" int insmos_rulebook_build_lg(const int32_t* out_coords, int64_t n_out
     if (!grid || !spec || !step) return INSMOS_ERR_INVALID_ARG;
     return rulebook_build_impl(out_coords, n_out, in_table, in_cap, nullptr, spec, TM, seg, entries, pair_count, stream,
                                nullptr, 0, 0, grid, grid_cap, step);
+}
+
+// insmos_rulebook_build_lg for the output tiles holding rows >= *first_row only (dead-row elimination)
+extern "C" int insmos_rulebook_build_lg_from(const int32_t* out_coords, int64_t n_out,
+                                             const insmos_slot_t* in_table, int64_t in_cap,
+                                             const void* grid, int64_t grid_cap, const int32_t* step,
+                                             const insmos_mapspec_t* spec, int32_t TM,
+                                             uint16_t* seg, uint32_t* entries, unsigned long long* pair_count,
+                                             const int32_t* first_row, void* stream) {
+    if (!grid || !spec || !step) return INSMOS_ERR_INVALID_ARG;
+    return rulebook_build_impl(out_coords, n_out, in_table, in_cap, nullptr, spec, TM, seg, entries, pair_count, stream,
+                               nullptr, 0, 0, grid, grid_cap, step, first_row);
 }

@@ -74,11 +74,18 @@ class CustomMinkUNet(nn.Module):
         layers += [block(self.inplanes, planes, stride=1, dilation=dilation, dimension=self.D) for _ in range(1, blocks)]
         return nn.Sequential(*layers)
 
-    def _cbr(self, conv, bn, x):
+    def _cbr(self, conv, bn, x, first_row=None):
         """conv -> BatchNorm -> ReLU; one fused kernel in eval mode."""
         if self.training:
             return bn(conv(x), relu=True)
-        return conv(x, bn=bn, relu=True)
+        return conv(x, bn=bn, relu=True, first_row=first_row)
+
+    @staticmethod
+    def _block(seq, x, rows):
+        """a _make_layer Sequential; with one BasicBlock (every level of this network) the dead-row bounds are passed down"""
+        if rows is not None and len(seq) == 1 and isinstance(seq[0], BasicBlock):
+            return seq[0](x, rows=rows)
+        return seq(x)
 
     def forward(self, x):                                       # minkunet.py:139-181
         # the strided coordinate maps are requested one level ahead of their first use, so that the host read of
@@ -91,10 +98,28 @@ class CustomMinkUNet(nn.Module):
         mgr.stride(k4, s, lazy=True)
         b2p4 = self.block2(self._cbr(self.conv2p2s2, self.bn2, b1p2))
         out = self.block3(self._cbr(self.conv3p4s2, self.bn3, b2p4))
-        out = self.block6(ME.cat(self._cbr(self.convtr5p8s2, self.bntr5, out), b2p4))
-        out = self.block7(ME.cat(self._cbr(self.convtr6p4s2, self.bntr6, out), b1p2))
-        out = self.block8(ME.cat(self._cbr(self.convtr7p2s2, self.bntr7, out), p1))
-        return self.final(out)
+        if self.training or not ops.USE_TPRUNE or self.D != 4 or not getattr(self, "newest_only", False):
+            out = self.block6(ME.cat(self._cbr(self.convtr5p8s2, self.bntr5, out), b2p4))
+            out = self.block7(ME.cat(self._cbr(self.convtr6p4s2, self.bntr6, out), b1p2))
+            out = self.block8(ME.cat(self._cbr(self.convtr7p2s2, self.bntr7, out), p1))
+            return self.final(out)
+        # Dead-row elimination.  The caller (MotionNet) consumes only the rows of the newest scan, time
+        # index 0 (motionnet.py:42-45).  A 3x3x3x3 convolution reaches one time index back, 1x1 / strided / transposed
+        # convolutions none (their kernels have extent 1 in time), so walking the decoder backwards from "rows with t >= 0":
+        #   final, block8.conv2 + downsample: t >= 0;  block8.conv1: t >= -1;  convtr7: t >= -2;
+        #   block7.conv2 + downsample: t >= -2;  block7.conv1: t >= -3;  convtr6: t >= -4;
+        #   block6.conv2 + downsample: t >= -4;  block6.conv1: t >= -5;  convtr5: t >= -6  (the encoder needs every row).
+        # starts[j] = first row with t >= -j per level, computed and kept ON THE DEVICE; kernels skip the tiles below it.
+        # Results on the needed rows are bit-identical (same per-row arithmetic); the other rows are left unwritten.
+        f1 = ops.time_row_starts(mgr.sets[x.coordinate_map_key])
+        f2 = ops.time_row_starts(mgr.sets[k2])
+        f4 = ops.time_row_starts(mgr.sets[k4])
+        r = lambda f, j: f[j:j + 1]                                         # noqa: E731
+        out = self._block(self.block6, ME.cat(self._cbr(self.convtr5p8s2, self.bntr5, out, r(f4, 6)), b2p4), (r(f4, 5), r(f4, 4), None))
+        out = self._block(self.block7, ME.cat(self._cbr(self.convtr6p4s2, self.bntr6, out, r(f2, 4)), b1p2), (r(f2, 3), r(f2, 2), None))
+        # the 3x3x3x3 map at tensor stride 1 is used by block8 only: it is BUILT for the rows t >= -1 only
+        out = self._block(self.block8, ME.cat(self._cbr(self.convtr7p2s2, self.bntr7, out, r(f1, 2)), p1), (r(f1, 1), r(f1, 0), r(f1, 1)))
+        return self.final(out, first_row=r(f1, 0))
 
 
 class MotionNet(nn.Module):
@@ -119,6 +144,7 @@ class MotionNet(nn.Module):
         mgr.sets[key] = voxels
         # every point carries the feature 0.5; the unweighted per-voxel average of 0.5s is 0.5 exactly
         feats = torch.full((voxels.n, 1), 0.5, dtype=torch.float32, device=pts.device)
+        self.MinkUNet.newest_only = True              # only the t == 0 rows of its output are read below
         pred = self.MinkUNet(ME.SparseTensor(feats, coordinate_manager=mgr, coordinate_map_key=key))
         # a5: slice back to points, keep the current scan, hstack(x,y,z,intensity, motion logits)
         if autograd.needs_grad(pred.F):

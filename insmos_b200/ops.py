@@ -383,7 +383,7 @@ def leafgrid_eligible(spec, step):
     return ncand <= 32 and spec.K <= 128
 
 
-def build_rulebook(out_set, in_set, spec, TM=None, parent=None, xstep=None, step=None):
+def build_rulebook(out_set, in_set, spec, TM=None, parent=None, xstep=None, step=None, first_row=None):
     """tiled rule book of the map in_set -> out_set.  step (optional): lattice step of in_set per dimension (tensor stride
     of a MinkowskiEngine level, 1 for spconv indices): eligible maps then probe the set's leaf grid (leafgrid()).  parent (int32 [n_out], optional): for a transposed map (mode-1
     spec) the row of every output (fine) row's coarse cell in in_set, as returned by unique_coords(q): the map is then
@@ -414,7 +414,11 @@ def build_rulebook(out_set, in_set, spec, TM=None, parent=None, xstep=None, step
     prof = _lib.PROFILE is not None
     if prof:
         _lib.NEXT_META = {"n_out": n_out, "K": K, "ncol": out_set.ncol}
-    if use_lg:
+    if use_lg and first_row is not None:
+        # dead-row elimination: only the tiles holding rows >= *first_row (device-side value) are built; the book is marked
+        call("insmos_rulebook_build_lg_from", _p(out_set.coords), n_out, _p(in_set.table), in_set.cap, _p(lgrid), lgcap,
+             _arr(C.c_int32, [int(v) for v in step]), C.byref(spec), TM, _p(seg), _p(entries), _p(pc), _p(first_row), _stream())
+    elif use_lg:
         call("insmos_rulebook_build_lg", _p(out_set.coords), n_out, _p(in_set.table), in_set.cap, _p(lgrid), lgcap,
              _arr(C.c_int32, [int(v) for v in step]), C.byref(spec), TM, _p(seg), _p(entries), _p(pc), _stream())
     elif use_xb:
@@ -430,6 +434,7 @@ def build_rulebook(out_set, in_set, spec, TM=None, parent=None, xstep=None, step
         call("insmos_rulebook_build", _p(out_set.coords), n_out, _p(in_set.table), in_set.cap, C.byref(spec), TM,
              _p(seg), _p(entries), _p(pc), None, _stream())
     rb = Rulebook(seg, entries, TM, K, n_out, in_set.n, pc)
+    rb.rows_from = first_row if (use_lg and first_row is not None) else None     # tiles below it were NOT built
     if prof:                               # bytes_alg = coordinate rows read + 8 B per pair written
         _lib.PROFILE[-1][3]["bytes"] = 4 * out_set.ncol * n_out + 8 * rb.num_pairs
         _lib.PROFILE[-1][3]["pairs"] = rb.num_pairs
@@ -437,7 +442,7 @@ def build_rulebook(out_set, in_set, spec, TM=None, parent=None, xstep=None, step
 
 
 # ---- feature ops --------------------------------------------------------------------------------
-def _epilogue(scale=None, shift=None, bias=None, residual=None, relu=False):
+def _epilogue(scale=None, shift=None, bias=None, residual=None, relu=False, first_row=None):
     """kernel epilogue: v*scale+shift, +bias, +residual, relu.  A conv bias followed by a fused BatchNorm means
     BN(conv + bias) = acc*scale + (shift + bias*scale): the bias is folded into the shift here so that the kernels'
     order (affine first, bias second) cannot apply it after the normalisation."""
@@ -454,6 +459,13 @@ def _epilogue(scale=None, shift=None, bias=None, residual=None, relu=False):
         else:
             setattr(ep, name, None)
     ep.relu = 1 if relu else 0
+    if first_row is not None:                       # device-side int32: rows below it may be left unwritten (dead-row hint)
+        if not (first_row.is_cuda and first_row.dtype == I32 and first_row.numel() >= 1):
+            raise TypeError("first_row: a CUDA int32 tensor with one element expected")
+        keep.append(first_row)
+        ep.first_row = first_row.data_ptr()
+    else:
+        ep.first_row = None
     return ep, keep
 
 
@@ -525,7 +537,7 @@ def prepared_weights(weight):
     return wf
 
 
-def sparse_conv(feat, weight, rb, scale=None, shift=None, bias=None, residual=None, relu=False, algo=0):
+def sparse_conv(feat, weight, rb, scale=None, shift=None, bias=None, residual=None, relu=False, algo=0, first_row=None):
     """out[n_out,Cout] = sum over rule-book pairs of feat[in] @ weight[k] (+ fused epilogue).
     weight [K,Cin,Cout] f32.  algo: 0/2 = tensor cores (3xTF32, fp32-accurate), 1 = SIMT fp32 reference path."""
     feat = _req(feat, F32, "sparse_conv")
@@ -535,7 +547,7 @@ def sparse_conv(feat, weight, rb, scale=None, shift=None, bias=None, residual=No
         raise ValueError("sparse_conv: shape mismatch (feat %s, weight %s, rule book K=%d n_in=%d)"
                          % (tuple(feat.shape), tuple(weight.shape), rb.K, rb.n_in))
     out = torch.empty((rb.n_out, Cout), dtype=F32, device=feat.device)
-    ep, keep = _epilogue(scale, shift, bias, residual, relu)
+    ep, keep = _epilogue(scale, shift, bias, residual, relu, first_row)
     if algo == 0:
         algo = DEFAULT_CONV_ALGO
         if algo == 2 and Cin < 8 and Cout % 4 == 0 and Cout <= 16:
@@ -573,14 +585,14 @@ def sparse_conv(feat, weight, rb, scale=None, shift=None, bias=None, residual=No
     return out
 
 
-def linear(feat, weight, scale=None, shift=None, bias=None, residual=None, relu=False):
+def linear(feat, weight, scale=None, shift=None, bias=None, residual=None, relu=False, first_row=None):
     """out = feat[n,Cin] @ weight[Cin,Cout] (+ fused epilogue)."""
     feat = _req(feat, F32, "linear")
     weight = _req(weight, F32, "linear")
     Cin, Cout = weight.shape
     n = feat.shape[0]
     out = torch.empty((n, Cout), dtype=F32, device=feat.device)
-    ep, keep = _epilogue(scale, shift, bias, residual, relu)
+    ep, keep = _epilogue(scale, shift, bias, residual, relu, first_row)
     call("insmos_linear_fwd", _p(feat), n, Cin, _p(weight), Cout, _p(out), C.byref(ep), _stream())
     return out
 
@@ -810,6 +822,17 @@ def mos_labels(logits, ignore_mask, label_map=None, want_confidence=True):
     conf = torch.empty((n, Cc - 1), dtype=F32, device=logits.device) if want_confidence else None
     call("insmos_mos_labels", _p(logits), n, Cc, int(ignore_mask), _p(label_map), _p(labels), _p(conf), _stream())
     return labels, conf
+
+
+USE_TPRUNE = _os.environ.get("INSMOS_TPRUNE", "1") != "0"
+
+
+def time_row_starts(cs, tcol=None):
+    """int32 [33] device tensor; element j (0..15) = smallest row of the CoordSet whose time coordinate is >= -j (n if none).
+    Slices [j:j+1] are the `first_row` hints of the convolutions (dead-row elimination)."""
+    out = torch.empty(33, dtype=I32, device=cs.coords.device)
+    call("insmos_time_row_starts", _p(cs.coords), cs.n, cs.ncol, cs.ncol - 1 if tcol is None else int(tcol), _p(out), _stream())
+    return out
 
 
 # ---- training step (SURVEY 8f N3): the pieces without a forward counterpart ------------------------------------------
