@@ -562,9 +562,19 @@ def sparse_conv(feat, weight, rb, scale=None, shift=None, bias=None, residual=No
             algo = 4 if (USE_UMMA and umma_eligible(K, Cin, Cout) and Cin % 8 == 0 and Cin >= 16) else 3
     wf = prepared_weights(weight) if algo == 2 else None
     if _lib.PROFILE is not None:          # algorithmic bytes / flops of this launch (SURVEY 8d formula)
-        P = rb.num_pairs
-        _lib.NEXT_META = {"bytes": 4 * (rb.n_in * Cin + rb.n_out * Cout) + 8 * P + 4 * K * Cin * Cout,
-                          "flops": 2 * P * Cin * Cout, "pairs": P, "K": K, "Cin": Cin, "Cout": Cout, "n_out": rb.n_out}
+        P, rows_out, rows_in = rb.num_pairs, rb.n_out, rb.n_in
+        if first_row is not None and algo == 2:
+            # dead-row hint honoured by this kernel: only the tiles from *first_row on are processed -- count THEIR rows and
+            # pairs (profiling mode only: this reads the bound back)
+            t0 = min(int(first_row[0].item()) // rb.TM, (rb.n_out + rb.TM - 1) // rb.TM)
+            n_tiles = (rb.n_out + rb.TM - 1) // rb.TM
+            segv = (rb.seg.view(torch.int16)[:n_tiles * (K + 1)].view(n_tiles, K + 1)[t0:, K].to(torch.int64) & 0xFFFF)
+            P = int(segv.sum().item())
+            rows_out = max(rb.n_out - t0 * rb.TM, 0)
+            rows_in = int(rb.n_in * (rows_out / max(rb.n_out, 1)))
+        _lib.NEXT_META = {"bytes": 4 * (rows_in * Cin + rows_out * Cout) + 8 * P + 4 * K * Cin * Cout,
+                          "flops": 2 * P * Cin * Cout, "pairs": P, "K": K, "Cin": Cin, "Cout": Cout, "n_out": rb.n_out,
+                          "rows_done": rows_out}
     if algo == 1:
         call("insmos_sparse_conv_fwd_ffma", _p(feat), rb.n_in, Cin, _p(weight), K, Cout, _p(rb.seg), _p(rb.entries), rb.TM,
              _p(out), rb.n_out, C.byref(ep), _stream())
