@@ -359,6 +359,11 @@ int insmos_boxes_to_voxel_units(const float* boxes7, const int32_t* labels, int3
 int insmos_box_membership(const int32_t* coords, int64_t n, const float* boxes8, int32_t nb, float mult,
                           float* out, int32_t out_stride, int32_t* first_hit, void* stream);
 
+/* iou3d_nms_utils.boxes_iou3d_gpu (models/bbox_post_process/iou3d_nms_utils.py:27-61, iou3d_nms_kernel.cu:236-249,377-387):
+ * iou [na, nb] of boxes [.,7] (x,y,z,dx,dy,dz,heading): rotated BEV overlap x height overlap over the union volume.  Used by
+ * the recall record of the 'eval' mode (models/post_process.py:66-109). */
+int insmos_boxes_iou3d(const float* boxes_a, int32_t na, const float* boxes_b, int32_t nb, float* iou, void* stream);
+
 /* ---- steps either side of the forward path ---------------------------- */
 
 /* N1 input staging (scripts/predict_mos.py:114-159 DemoDataset.__getitem__, :161-166 transform_point_cloud, :174-179

@@ -97,6 +97,7 @@ PROTOTYPES = {
     "insmos_nms_rotated_pairs": (C.c_int, [_P, _I32, _F, _I32, _P, _P, _I64, _P, _P, _P, _P]),
     "insmos_boxes_to_voxel_units": (C.c_int, [_P, _P, _I32, C.POINTER(_F), C.POINTER(_F), _F, _P, _P]),
     "insmos_box_membership": (C.c_int, [_P, _I64, _P, _I32, _F, _P, _I32, _P, _P]),
+    "insmos_boxes_iou3d": (C.c_int, [_P, _I32, _P, _I32, _P, _P]),
     "insmos_time_row_starts": (C.c_int, [_P, _I64, _I32, _I32, _P, _P]),
     "insmos_rulebook_build_lg_from": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, C.POINTER(_I32), C.POINTER(MapSpec), _I32, _P, _P, _P, _P, _P]),
     # training step (N3)
@@ -162,7 +163,7 @@ KERNELS_PER_CALL = {
     "insmos_xblock_build": 2, "insmos_leafgrid_build": 1, "insmos_rulebook_build_lg": 1, "insmos_rulebook_build_xb": 1, "insmos_rulebook_build_up": 1,
     "insmos_sparse_conv_fwd_umma": 1, "insmos_conv2d_nhwc_umma": 1, "insmos_conv2d_nhwc_tcgen05": 1,
     "insmos_conv_prep_weights_umma": 1, "insmos_bev_prep_weights_tcgen05": 1, "insmos_dense_scatter_nhwc": 1,
-    "insmos_time_row_starts": 2, "insmos_rulebook_build_lg_from": 1, "insmos_sparse_conv_wgrad": 2, "insmos_column_moments": 1, "insmos_bn_train_finalize": 1, "insmos_bn_bwd_apply": 1, "insmos_scatter_add_rows": 1,
+"insmos_boxes_iou3d": 1, "insmos_time_row_starts": 2, "insmos_rulebook_build_lg_from": 1, "insmos_sparse_conv_wgrad": 2, "insmos_column_moments": 1, "insmos_bn_train_finalize": 1, "insmos_bn_bwd_apply": 1, "insmos_scatter_add_rows": 1,
     "insmos_center_targets": 1, "insmos_adam_step": 1,
 }
 PROFILE = None        # list collecting (name, start_event, end_event, meta) when profiling is on

@@ -192,6 +192,8 @@ k_spconv_tc4(TcArgs p) {
 }
 
 static int choose_wpt(const TcArgs& a, int NT) {
+    // (sizing the warps per tile for the ACTIVE tiles of a dead-row launch was measured and changed nothing: 1.29 vs 1.34 ms for
+    // the family; it also changes the grouping of the partial sums, so the launches keep the full-grid choice and stay bit-identical)
     const int64_t units = a.n_tiles * a.groups;
     int wpt = 1;
     while (wpt < 8 && units * wpt < 8192 && wpt * 2 <= a.K) wpt *= 2;

@@ -134,6 +134,31 @@ __device__ __forceinline__ float rot_iou_bev(const float* A, const float* B) {
     return so / fmaxf(sa + sb - so, 1e-8f);
 }
 
+// iou3d_nms_utils.boxes_iou3d_gpu (iou3d_nms_utils.py:27-61) in one kernel: rotated BEV overlap (iou3d_nms_kernel.cu:236-249)
+// x height overlap / (vol_a + vol_b - overlap), the torch expressions in their fp32 order.  One thread per (a, b) pair.
+__global__ void k_boxes_iou3d(const float* __restrict__ a, int na, const float* __restrict__ b, int nb, float* __restrict__ iou) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= na || j >= nb) return;
+    const float* A = a + (size_t)i * 7;
+    const float* B = b + (size_t)j * 7;
+    const float bev = rot_overlap(A, B);
+    const float a_max = A[2] + A[5] / 2.0f, a_min = A[2] - A[5] / 2.0f;
+    const float b_max = B[2] + B[5] / 2.0f, b_min = B[2] - B[5] / 2.0f;
+    const float h = fmaxf(fminf(a_max, b_max) - fmaxf(a_min, b_min), 0.0f);
+    const float o3d = bev * h;
+    const float va = A[3] * A[4] * A[5], vb = B[3] * B[4] * B[5];
+    iou[(size_t)i * nb + j] = o3d / fmaxf(va + vb - o3d, 1e-6f);
+}
+
+extern "C" int insmos_boxes_iou3d(const float* boxes_a, int32_t na, const float* boxes_b, int32_t nb, float* iou, void* stream) {
+    if (na < 0 || nb < 0 || (na > 0 && nb > 0 && (!boxes_a || !boxes_b || !iou))) return INSMOS_ERR_INVALID_ARG;
+    if (na == 0 || nb == 0) return INSMOS_OK;
+    const dim3 threads(16, 16), blocks((nb + 15) / 16, (na + 15) / 16);
+    k_boxes_iou3d<<<blocks, threads, 0, (cudaStream_t)stream>>>(boxes_a, na, boxes_b, nb, iou);
+    INSMOS_CHECK_LAUNCH("k_boxes_iou3d");
+    return INSMOS_OK;
+}
+
 // mask[i*cb + c] bit j = IoU(box i, box c*64+j) > thresh, only for j > i (iou3d_nms_kernel.cu:267-311)
 __global__ void __launch_bounds__(64)
 k_nms_mask(const float* __restrict__ boxes, int n, float thresh, unsigned long long* __restrict__ mask) {

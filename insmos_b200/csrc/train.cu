@@ -10,48 +10,56 @@
 // wgrad:  dW[k][ci][co] = sum over the pairs (i, o) of bucket k of  x[i][ci] * dy[o][co]
 //
 // grid = (K, S, ceil(Cin / CIB)); a block owns offset k, the tiles t = s, s + S, ... of slice s and CIB input channels.
-// Warp w of the block walks the tiles  s + S * (w + 8 j): the pairs of bucket (tile, k) are taken G at a time
-// (G = 32 / CoutP lane groups, lane = (g, co)); a lane keeps acc[CIB][M] for its output channels co + 32 m: per pair one
-// coalesced load of the dy row, CIB / 4 broadcast float4 loads of the x row, CIB * M FFMAs.  The lane groups are then
-// summed by shuffles, the warps through shared memory (fixed order), and the block writes ITS partial matrix
-// partial[s][k][ci][co]; k_wgrad_reduce adds the S partials in slice order -- no atomics, the result does not depend on
-// scheduling.
+// Warp w of the block walks the tiles  s + S * (w + 8 j).  A lane owns FOUR consecutive output channels (one float4 of the dy
+// row) and CIB input channels: acc[CIB][4]; LPG = CoutP / 4 lanes cover a row, so a warp takes G = 32 / LPG pairs side by side
+// and U of them in flight per lane: per pair and lane 1 float4 of dy + CIB / 4 float4 of x (the lanes of a group read the same
+// x row: one sector each) feed 4 * CIB FFMAs.  First version (one channel per lane, profiles/r02_train_calls.jsonl): 5 loads per
+// 16 FFMAs and one pair per warp at Cout = 32 -- 1.7-5 TFLOP/s on the MotionNet layers.
+// The lane groups are then summed by shuffles, the warps through shared memory (fixed order), and the block writes ITS
+// partial matrix partial[s][k][ci][co]; k_wgrad_reduce adds the S partials in slice order -- no atomics, the result does not
+// depend on scheduling.
 #define WG_CIB 16
 #define WG_WARPS 8
-template <int M, int U>
+template <int U>
 __global__ void __launch_bounds__(WG_WARPS * 32)
 k_spconv_wgrad(const float* __restrict__ x, const float* __restrict__ dy, const uint16_t* __restrict__ seg,
-               const uint32_t* __restrict__ entries, int TM, int K, int Cin, int Cout, int CoutP, int64_t n_tiles, int S,
-               float* __restrict__ partial) {
+               const uint32_t* __restrict__ entries, int TM, int K, int Cin, int Cout, int LPG, int64_t n_tiles, int S,
+               int aligned, float* __restrict__ partial) {
     __shared__ float red[WG_WARPS][WG_CIB][33];
     const int k = blockIdx.x, s = blockIdx.y, ci0 = blockIdx.z * WG_CIB;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int G = 32 / CoutP, g = lane / CoutP, c0 = lane - g * CoutP;
-    float acc[WG_CIB][M];
+    const int G = 32 / LPG, g = lane / LPG, cq = lane - g * LPG;       // pair group, channel quad of this lane
+    const int c0 = 4 * cq;
+    float acc[WG_CIB][4];
 #pragma unroll
     for (int a = 0; a < WG_CIB; ++a)
 #pragma unroll
-        for (int m = 0; m < M; ++m) acc[a][m] = 0.0f;
-    const bool vec = (Cin & 3) == 0 && ci0 + WG_CIB <= Cin;            // rows of x are 16-byte aligned multiples
+        for (int q = 0; q < 4; ++q) acc[a][q] = 0.0f;
+    const bool xvec = (aligned & 1) && (Cin & 3) == 0 && ci0 + WG_CIB <= Cin;      // x rows: 16-byte aligned float4 chunks
+    const bool dvec = (aligned & 2) && (Cout & 3) == 0;                             // dy rows likewise
     for (int64_t tile = s + (int64_t)S * warp; tile < n_tiles; tile += (int64_t)S * WG_WARPS) {
         const uint16_t* tseg = seg + tile * (K + 1);
         const int start = tseg[k], n = (int)tseg[k + 1] - start;
         const uint32_t* tent = entries + tile * (int64_t)TM * K + start;
-        // U pairs per lane in flight: first the U rule-book entries, then all their row loads, then the FFMAs -- the two
-        // dependent global-load latencies (entry -> rows) are paid once per U pairs instead of once per pair
         for (int p0 = 0; p0 < n; p0 += G * U) {
             uint32_t e[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) { const int p = p0 + g + G * u; e[u] = p < n ? __ldg(tent + p) : 0xffffffffu; }
-            float d[U][M], xv[U][WG_CIB];
+            float d[U][4], xv[U][WG_CIB];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const bool ok = e[u] != 0xffffffffu;
                 const int64_t i = ok ? (int64_t)(e[u] & INSMOS_ROW_MASK) : 0, o = ok ? tile * TM + (e[u] >> INSMOS_ROW_BITS) : 0;
+                const float* dr = dy + o * Cout + c0;
+                if (dvec) {
+                    const float4 v = (ok && c0 < Cout) ? __ldg(reinterpret_cast<const float4*>(dr)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    d[u][0] = v.x; d[u][1] = v.y; d[u][2] = v.z; d[u][3] = v.w;
+                } else {
 #pragma unroll
-                for (int m = 0; m < M; ++m) { const int co = c0 + 32 * m; d[u][m] = (ok && co < Cout) ? __ldg(dy + o * Cout + co) : 0.0f; }
+                    for (int q = 0; q < 4; ++q) d[u][q] = (ok && c0 + q < Cout) ? __ldg(dr + q) : 0.0f;
+                }
                 const float* xr = x + i * Cin + ci0;
-                if (vec) {
+                if (xvec) {
 #pragma unroll
                     for (int q = 0; q < WG_CIB / 4; ++q) {
                         const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(xr) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -67,23 +75,23 @@ k_spconv_wgrad(const float* __restrict__ x, const float* __restrict__ dy, const 
 #pragma unroll
                 for (int a = 0; a < WG_CIB; ++a)
 #pragma unroll
-                    for (int m = 0; m < M; ++m) acc[a][m] = __fmaf_rn(xv[u][a], d[u][m], acc[a][m]);
+                    for (int q = 0; q < 4; ++q) acc[a][q] = __fmaf_rn(xv[u][a], d[u][q], acc[a][q]);
         }
     }
-    // lane groups -> group 0 (fixed shuffle tree), then per 32-channel slab m: warps -> shared memory -> fixed-order sum
+    // lane groups -> group 0 (fixed shuffle tree), then per channel-of-the-quad q: warps -> shared memory -> fixed-order sum
     float* dst = partial + (((size_t)s * K + k) * Cin) * Cout;
 #pragma unroll
-    for (int m = 0; m < M; ++m) {
+    for (int q = 0; q < 4; ++q) {
 #pragma unroll
         for (int a = 0; a < WG_CIB; ++a) {
-            float v = acc[a][m];
-            for (int off = 16; off >= CoutP; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-            if (g == 0) red[warp][a][c0] = v;
+            float v = acc[a][q];
+            for (int off = 16; off >= LPG; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            if (g == 0) red[warp][a][cq] = v;
         }
         __syncthreads();
         for (int idx = threadIdx.x; idx < WG_CIB * 32; idx += blockDim.x) {
-            const int a = idx >> 5, c = idx & 31, co = c + 32 * m;
-            if (ci0 + a >= Cin || co >= Cout || c >= CoutP) continue;
+            const int a = idx >> 5, c = idx & 31, co = 4 * c + q;
+            if (ci0 + a >= Cin || co >= Cout || c >= LPG) continue;
             float v = 0.0f;
 #pragma unroll
             for (int w = 0; w < WG_WARPS; ++w) v += red[w][a][c];
@@ -125,17 +133,12 @@ extern "C" int insmos_sparse_conv_wgrad(const float* in, int64_t n_in, int32_t C
         INSMOS_CHECK_CUDA(cudaMemsetAsync(dweight, 0, sizeof(float) * n, st));
         return INSMOS_OK;
     }
-    int CoutP = 1;
-    while (CoutP < Cout && CoutP < 32) CoutP <<= 1;
-    const int M = (Cout + 31) / 32;
+    int LPG = 1;                                                          // lanes per row: next power of two >= ceil(Cout / 4)
+    while (LPG * 4 < Cout) LPG <<= 1;
     const int64_t n_tiles = ceil_div64(n_out, TM);
     const dim3 grid((unsigned)K, (unsigned)S, (unsigned)((Cin + WG_CIB - 1) / WG_CIB));
-    switch (M) {
-        case 1: k_spconv_wgrad<1, 4><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, CoutP, n_tiles, S, partial); break;
-        case 2: k_spconv_wgrad<2, 4><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, CoutP, n_tiles, S, partial); break;
-        case 3: k_spconv_wgrad<3, 2><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, CoutP, n_tiles, S, partial); break;
-        default: k_spconv_wgrad<4, 2><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, CoutP, n_tiles, S, partial); break;
-    }
+    const int aligned = ((reinterpret_cast<uintptr_t>(in) & 15) == 0 ? 1 : 0) | ((reinterpret_cast<uintptr_t>(dout) & 15) == 0 ? 2 : 0);
+    k_spconv_wgrad<2><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, LPG, n_tiles, S, aligned, partial);
     INSMOS_CHECK_LAUNCH("k_spconv_wgrad");
     k_wgrad_reduce<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(partial, S, n, dweight);
     INSMOS_CHECK_LAUNCH("k_wgrad_reduce");

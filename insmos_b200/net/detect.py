@@ -24,8 +24,39 @@ def class_agnostic_nms(scores, boxes, nms_config, score_thresh):
     return cand[top_i[order[keep.long()]]]
 
 
+def generate_recall_record(box_preds, recall_dict, batch_index, data_dict=None, thresh_list=None):
+    """post_process.py:66-109: per IoU threshold, how many ground-truth boxes are matched by a prediction with IoU3D above
+    it.  Same dictionary ('gt', 'roi_<t>', 'rcnn_<t>'); the pairwise IoU runs in insmos_boxes_iou3d and the per-threshold
+    counts come back in ONE read (the reference reads one scalar per threshold)."""
+    if "gt_boxes" not in data_dict:
+        return recall_dict
+    gt_boxes = data_dict["gt_boxes"][batch_index]
+    if len(recall_dict) == 0:
+        recall_dict = {"gt": 0}
+        for t in thresh_list:
+            recall_dict["roi_%s" % str(t)] = 0
+            recall_dict["rcnn_%s" % str(t)] = 0
+    k = len(gt_boxes) - 1
+    nonzero = (gt_boxes.sum(dim=1) != 0).tolist() if len(gt_boxes) else []
+    while k > 0 and not nonzero[k]:                          # trailing all-zero padding rows (post_process.py:82-85)
+        k -= 1
+    cur_gt = gt_boxes[:k + 1]
+    if cur_gt.shape[0] > 0:
+        if box_preds.shape[0] > 0:
+            iou = ops.boxes_iou3d(box_preds[:, 0:7].contiguous(), cur_gt[:, 0:7].float().contiguous())
+            best = iou.max(dim=0)[0]
+            counts = torch.stack([(best > t).sum() for t in thresh_list]).tolist()
+        else:
+            counts = [0] * len(thresh_list)
+        for t, c in zip(thresh_list, counts):
+            recall_dict["rcnn_%s" % str(t)] += int(c)
+        recall_dict["gt"] += int(cur_gt.shape[0])
+    return recall_dict
+
+
 def post_processing(batch_dict, cfg, num_class):
-    """test/eval-mode post_processing for batch 1 -> ([{'pred_boxes','pred_scores','pred_labels'}], {})"""
+    """post_processing for batch 1 -> ([{'pred_boxes','pred_scores','pred_labels'}], recall dict); the recall record is
+    filled whenever the sample carries 'gt_boxes', as in the reference (post_process.py:206-216)."""
     boxes, scores, labels = batch_dict["_decoded"]
     if cfg["NMS_CONFIG"]["MULTI_CLASSES_NMS"]:
         raise NotImplementedError("MULTI_CLASSES_NMS is disabled in the reference config (config.yaml:152)")
@@ -34,7 +65,10 @@ def post_processing(batch_dict, cfg, num_class):
     if cfg.get("OUTPUT_RAW_SCORE", False):
         final_scores = batch_dict["batch_cls_preds"][0].max(dim=-1)[0][sel]
     rec = {"pred_boxes": boxes[sel], "pred_scores": final_scores, "pred_labels": labels[sel].long()}
-    return [rec], {}
+    recall = {}
+    if "gt_boxes" in batch_dict and batch_dict.get("_want_recall", False):
+        recall = generate_recall_record(rec["pred_boxes"], recall, 0, data_dict=batch_dict, thresh_list=cfg["RECALL_THRESH_LIST"])
+    return [rec], recall
 
 
 class InstanceBoxes:

@@ -101,11 +101,10 @@ class InsMOS_Model(nn.Module):
     def forward(self, list_batch_dict, Model_mode):
         if Model_mode == "train":
             return self.forward_train(list_batch_dict)
+        if Model_mode == "eval":
+            return self.forward_eval(list_batch_dict)
         if Model_mode != "test":
-            # 'eval' returns the per-sample recall records of generate_recall_record (models/models.py:331-359), which need
-            # boxes_iou3d_gpu (not built).  Returning empty recall dicts would let a reference validation_step log garbage
-            # silently, so the mode refuses.
-            raise NotImplementedError("Model_mode %r: 'test' (inference) and 'train' are implemented" % Model_mode)
+            raise ValueError("Model_mode %r: 'train', 'eval' or 'test'" % (Model_mode,))
         boxes_out, recall_out, logits_out = [], [], []
         for batch_dict in list_batch_dict:
             batch_dict = self.motion_encoder(batch_dict)
@@ -145,7 +144,36 @@ def _forward_train(self, list_batch_dict):
     return loss / len(list_batch_dict), train_loss_dict, gt_list, pred_list
 
 
+def _forward_eval(self, list_batch_dict):
+    """models/models.py:301-306,349-359,370-373: the inference forward plus the validation losses (MOS loss of both heads) and
+    the per-sample recall record.  Returns (preb_dict_list, recall_dict_list, gt_list, pred_list, val_loss float,
+    val_motion_loss tensor [1]) like the reference."""
+    dev = list_batch_dict[0]["past_point_clouds"].device
+    val_loss = torch.zeros(1, device=dev)
+    val_motion_loss = torch.zeros(1, device=dev)
+    boxes_out, recall_out, gt_list, pred_list = [], [], [], []
+    for batch_dict in list_batch_dict:
+        batch_dict = self.motion_encoder(batch_dict)
+        if not self.use_motion_loss:
+            batch_dict["current_motion_feature"] = batch_dict["current_motion_feature"][:, :3]
+        gt = batch_dict["past_labels"][-1]
+        loss_motion = self.MOSLoss.compute_loss(batch_dict["current_motion_feature"].clone(), gt)
+        batch_dict = self.voxel_generate(batch_dict)
+        batch_dict = self.vfe(batch_dict)
+        batch_dict["_want_recall"] = True
+        point_seg, pred_dicts, recall_dicts = self.unet(batch_dict, "eval")
+        val_loss = val_loss + self.MOSLoss.compute_loss(point_seg, gt)
+        val_motion_loss = val_motion_loss + loss_motion.detach()
+        boxes_out.append(pred_dicts)
+        recall_out.append(recall_dicts)
+        gt_list.append(gt)
+        pred_list.append(point_seg)
+    n = len(list_batch_dict)
+    return boxes_out, recall_out, gt_list, pred_list, (val_loss / n).item(), val_motion_loss / n
+
+
 InsMOS_Model.forward_train = _forward_train
+InsMOS_Model.forward_eval = _forward_eval
 
 
 class ClassificationMetrics(nn.Module):

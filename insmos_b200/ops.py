@@ -777,6 +777,17 @@ def nms_rotated(boxes_sorted, thresh, max_keep, dense=None):
     return keep[:int(num.item())]
 
 
+def boxes_iou3d(boxes_a, boxes_b):
+    """iou3d_nms_utils.boxes_iou3d_gpu: boxes [N,7], [M,7] -> IoU3D [N,M]."""
+    boxes_a = _req(boxes_a, F32, "boxes_iou3d")
+    boxes_b = _req(boxes_b, F32, "boxes_iou3d")
+    if boxes_a.shape[1] != 7 or boxes_b.shape[1] != 7:
+        raise ValueError("boxes_iou3d: [N,7] boxes (x,y,z,dx,dy,dz,heading) expected")
+    out = torch.zeros((boxes_a.shape[0], boxes_b.shape[0]), dtype=F32, device=boxes_a.device)
+    call("insmos_boxes_iou3d", _p(boxes_a), boxes_a.shape[0], _p(boxes_b), boxes_b.shape[0], _p(out), _stream())
+    return out
+
+
 def boxes_to_voxel_units(boxes7, labels, range_min, vsize, stride):
     boxes7 = _req(boxes7, F32, "boxes_to_voxel_units")
     labels = _req(labels, I32, "boxes_to_voxel_units")

@@ -212,6 +212,40 @@ def post_process(cls_preds, box_preds):
             "n_cand": int(mask.sum()), "all_scores": scores, "all_boxes": boxes, "all_labels": labels}
 
 
+def boxes_iou3d(a, b):
+    """iou3d_nms_utils.py:27-61 (boxes_iou3d_gpu) in fp32: BEV overlap x height overlap / union volume.  a [N,7], b [M,7]."""
+    f = np.float32
+    a, b = np.asarray(a, dtype=f), np.asarray(b, dtype=f)
+    bev = native.overlap_matrix(a[:, :7], b[:, :7])
+    a_max, a_min = (a[:, 2] + a[:, 5] / f(2))[:, None], (a[:, 2] - a[:, 5] / f(2))[:, None]
+    b_max, b_min = (b[:, 2] + b[:, 5] / f(2))[None, :], (b[:, 2] - b[:, 5] / f(2))[None, :]
+    h = np.maximum(np.minimum(a_max, b_max) - np.maximum(a_min, b_min), f(0))
+    o3d = bev * h
+    va, vb = (a[:, 3] * a[:, 4] * a[:, 5])[:, None], (b[:, 3] * b[:, 4] * b[:, 5])[None, :]
+    return o3d / np.maximum(va + vb - o3d, f(1e-6))
+
+
+def recall_record(pred_boxes, gt_boxes, thresh_list=(0.3, 0.5, 0.7)):
+    """post_process.py:66-109 for one sample without rois: {'gt', 'roi_<t>': 0, 'rcnn_<t>'}"""
+    rec = {"gt": 0}
+    for t in thresh_list:
+        rec["roi_%s" % str(t)] = 0
+        rec["rcnn_%s" % str(t)] = 0
+    gt = np.asarray(gt_boxes, dtype=np.float32)
+    k = len(gt) - 1
+    while k > 0 and gt[k].sum() == 0:
+        k -= 1
+    gt = gt[:k + 1]
+    if len(gt) > 0:
+        pb = np.asarray(pred_boxes, dtype=np.float32)
+        if len(pb) > 0:
+            best = boxes_iou3d(pb[:, :7], gt[:, :7]).max(axis=0)
+            for t in thresh_list:
+                rec["rcnn_%s" % str(t)] += int((best > np.float32(t)).sum())
+        rec["gt"] += len(gt)
+    return rec
+
+
 def instance_bits(ind, boxes8):
     xyz = np.ascontiguousarray(np.asarray(ind)[:, [3, 2, 1]], dtype=np.int32)
     return torch.from_numpy(native.find_features_by_bbox_with_yaw(xyz, boxes8.numpy())).float()

@@ -32,6 +32,19 @@ def lib():
     return _lib
 
 
+def overlap_matrix(a, b):
+    """rotated BEV overlap AREA of every pair (iou3d_nms_kernel.cu:104-225 box_overlap, :236-249 boxes_overlap_kernel)."""
+    a = np.ascontiguousarray(a, dtype=np.float32); b = np.ascontiguousarray(b, dtype=np.float32)
+    L = lib()
+    L.oracle_box_overlap.restype = C.c_float
+    L.oracle_box_overlap.argtypes = [C.c_void_p, C.c_void_p]
+    out = np.zeros((len(a), len(b)), dtype=np.float32)
+    for i in range(len(a)):
+        for j in range(len(b)):
+            out[i, j] = L.oracle_box_overlap(a[i].ctypes.data, b[j].ctypes.data)
+    return out
+
+
 def iou_matrix(a, b):
     a = np.ascontiguousarray(a, dtype=np.float32); b = np.ascontiguousarray(b, dtype=np.float32)
     out = np.zeros((len(a), len(b)), dtype=np.float32)

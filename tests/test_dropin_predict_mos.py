@@ -133,8 +133,8 @@ def test_lightning_checkpoint_loads_strictly_through_the_reference_call(dropin):
     for k in ("model.motion_encoder.MinkUNet.conv0p1s1.kernel", "model.unet.conv_input.0.weight", "model.unet.mos_seg_layer.bias"):
         assert torch.equal(got[k], sd[k])
     assert model.hparams["MODEL"]["DENSE_HEAD"]["NUM_CLASS"] == 3
-    with pytest.raises(NotImplementedError):
-        model.forward([], "eval")                              # recall records need boxes_iou3d_gpu: refuses instead of logging garbage
+    with pytest.raises(ValueError):
+        model.forward([], "validate")                          # the three modes of the reference: 'train', 'eval', 'test'
     with pytest.raises(RuntimeError):
         model.forward([], "train")                             # 'train' is implemented (N3) but needs model.train()
     with pytest.raises(RuntimeError):                          # no CPU fallback: the script's .cuda() is mandatory

@@ -35,6 +35,22 @@ def test_iou_matrix_matches_reference_cpu_twin():
     assert abs(native.iou_matrix(sq, half)[0, 0] - 1.0 / 3.0) < 2e-2
 
 
+def test_overlap_and_iou3d_are_consistent_with_the_pinned_bev_iou():
+    """oracle.graph.boxes_iou3d (recall record of the 'eval' mode) rests on the same box_overlap the pinned BEV IoU uses"""
+    from oracle import graph
+    rng = np.random.default_rng(2)
+    a, b = _boxes(rng, 60, 6.0), _boxes(rng, 70, 6.0)
+    ov, iou = native.overlap_matrix(a, b), native.iou_matrix(a, b)
+    sa, sb = (a[:, 3] * a[:, 4])[:, None], (b[:, 3] * b[:, 4])[None, :]
+    assert np.array_equal(iou, ov / np.maximum(sa + sb - ov, np.float32(1e-8)))
+    cube = np.array([[0, 0, 0, 2, 2, 2, 0]], np.float32)
+    up = np.array([[0, 0, 1, 2, 2, 2, 0]], np.float32)                    # shifted by half its height: IoU3D = 1/3
+    assert abs(graph.boxes_iou3d(cube, up)[0, 0] - 1.0 / 3.0) < 2e-2
+    assert graph.boxes_iou3d(cube, np.array([[0, 0, 5, 2, 2, 2, 0]], np.float32))[0, 0] == 0.0
+    rec = graph.recall_record(np.concatenate([cube, up]), np.array([[0, 0, 0, 2, 2, 2, 0, 1], [9, 9, 0, 2, 2, 2, 0, 2], [0] * 8], np.float32))
+    assert rec == {"gt": 2, "roi_0.3": 0, "rcnn_0.3": 1, "roi_0.5": 0, "rcnn_0.5": 1, "roi_0.7": 0, "rcnn_0.7": 1}
+
+
 def test_array_index_matches_reference():
     ai = native.ref_array_index()
     if ai is None:
