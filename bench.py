@@ -66,14 +66,17 @@ def source_digest():
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
-    def __init__(self, index):
+    def __init__(self, index, enabled=True, interval=0.25):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        # ONE sampler per job (rank 0, its own GPU): eight ranks polling nvidia-smi at 10 Hz serialise on the driver and on the
+        # host cores the launch threads need (8-GPU run: 6.86 ms/step with every rank sampling)
+        self.enabled, self.interval = enabled, interval
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
+        while self.enabled and not self.stop_flag:
             try:
                 r = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                    capture_output=True, text=True, timeout=5)
@@ -82,7 +85,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append(f)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(self.interval)
 
     def summary(self):
         if not self.samples:
@@ -243,7 +246,7 @@ def run_train(args, device, rank, local_rank, world, out_stream):
     losses = [ts.step(batch(i)) for i in range(warmup)]
     gc.collect()
     gc.disable()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, enabled=(rank == 0))
     sampler.start()
     torch.cuda.synchronize()
     if dist:
@@ -318,6 +321,24 @@ def run_train(args, device, rank, local_rank, world, out_stream):
         dist.destroy_process_group()
 
 
+def bind_to_gpu_cpus(index):
+    """pin this process to the CPU cores the driver reports as local to GPU `index` (NUMA node of its PCIe root): with one
+    process per GPU and no binding, half of the ranks of an 8-GPU box queue their launches from the remote socket."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_cpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def _claim_stdout():
     """stdout carries exactly ONE JSON line: everything else any library writes to fd 1 (NCCL's version banner, torchrun
     notices) is sent to stderr; returns the stream that still points at the real stdout."""
@@ -350,6 +371,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU port)")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    bound = bind_to_gpu_cpus(local_rank) if world > 1 else 0
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     if args.workload == "c4":
@@ -476,7 +498,7 @@ def main():
         finally:
             gc.enable()
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, enabled=(rank == 0))
     sampler.start()
     regions, launches, out = timed(False)
     sampler.stop_flag = True
@@ -568,7 +590,7 @@ def main():
                        "l2": "no explicit flush: each step streams > 126 MB (rule books + features) and inputs rotate over %d distinct clouds" % n_clouds,
                        "arithmetic": "fp32; sparse-conv products on tensor cores as 3xTF32 (fp32-accurate) or fp32 FFMA; cuDNN TF32 off",
                        "weights": "tests/golden/insmos_c2.npz (the C2 parity golden's weights)",
-                       "streams": args.streams,
+                       "streams": args.streams, "cpus_bound_per_rank": bound,
                        "points_per_step": int(dev[0].shape[0]), "current_points": n_cur},
             "timing": {"regions": len(regions), "steps_per_region": args.steps, "timed_s": round(sum(regions) / 1000.0, 3),
                        "ms_per_step_median": round(ms / args.steps, 4), "ms_per_step_min": round(min(regions) / args.steps, 4),
