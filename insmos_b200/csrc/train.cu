@@ -20,22 +20,23 @@
 // depend on scheduling.
 #define WG_CIB 16
 #define WG_WARPS 8
-template <int U>
+// CIB = input channels per block: 16, or 8 for the 8-channel layers / 4 for 1..4 channels (no padded accumulators; more pairs in flight)
+template <int U, int CIB>
 __global__ void __launch_bounds__(WG_WARPS * 32)
 k_spconv_wgrad(const float* __restrict__ x, const float* __restrict__ dy, const uint16_t* __restrict__ seg,
                const uint32_t* __restrict__ entries, int TM, int K, int Cin, int Cout, int LPG, int64_t n_tiles, int S,
                int aligned, float* __restrict__ partial) {
-    __shared__ float red[WG_WARPS][WG_CIB][33];
-    const int k = blockIdx.x, s = blockIdx.y, ci0 = blockIdx.z * WG_CIB;
+    __shared__ float red[WG_WARPS][CIB][33];
+    const int k = blockIdx.x, s = blockIdx.y, ci0 = blockIdx.z * CIB;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int G = 32 / LPG, g = lane / LPG, cq = lane - g * LPG;       // pair group, channel quad of this lane
     const int c0 = 4 * cq;
-    float acc[WG_CIB][4];
+    float acc[CIB][4];
 #pragma unroll
-    for (int a = 0; a < WG_CIB; ++a)
+    for (int a = 0; a < CIB; ++a)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[a][q] = 0.0f;
-    const bool xvec = (aligned & 1) && (Cin & 3) == 0 && ci0 + WG_CIB <= Cin;      // x rows: 16-byte aligned float4 chunks
+    const bool xvec = (aligned & 1) && (Cin & 3) == 0 && ci0 + CIB <= Cin;      // x rows: 16-byte aligned float4 chunks
     const bool dvec = (aligned & 2) && (Cout & 3) == 0;                             // dy rows likewise
     for (int64_t tile = s + (int64_t)S * warp; tile < n_tiles; tile += (int64_t)S * WG_WARPS) {
         const uint16_t* tseg = seg + tile * (K + 1);
@@ -45,7 +46,7 @@ k_spconv_wgrad(const float* __restrict__ x, const float* __restrict__ dy, const 
             uint32_t e[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) { const int p = p0 + g + G * u; e[u] = p < n ? __ldg(tent + p) : 0xffffffffu; }
-            float d[U][4], xv[U][WG_CIB];
+            float d[U][4], xv[U][CIB];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const bool ok = e[u] != 0xffffffffu;
@@ -61,19 +62,19 @@ k_spconv_wgrad(const float* __restrict__ x, const float* __restrict__ dy, const 
                 const float* xr = x + i * Cin + ci0;
                 if (xvec) {
 #pragma unroll
-                    for (int q = 0; q < WG_CIB / 4; ++q) {
+                    for (int q = 0; q < CIB / 4; ++q) {
                         const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(xr) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
                         xv[u][4 * q] = v.x; xv[u][4 * q + 1] = v.y; xv[u][4 * q + 2] = v.z; xv[u][4 * q + 3] = v.w;
                     }
                 } else {
 #pragma unroll
-                    for (int a = 0; a < WG_CIB; ++a) xv[u][a] = (ok && ci0 + a < Cin) ? __ldg(xr + a) : 0.0f;
+                    for (int a = 0; a < CIB; ++a) xv[u][a] = (ok && ci0 + a < Cin) ? __ldg(xr + a) : 0.0f;
                 }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u)                                 // fixed order: the sum does not depend on scheduling
 #pragma unroll
-                for (int a = 0; a < WG_CIB; ++a)
+                for (int a = 0; a < CIB; ++a)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) acc[a][q] = __fmaf_rn(xv[u][a], d[u][q], acc[a][q]);
         }
@@ -83,13 +84,13 @@ k_spconv_wgrad(const float* __restrict__ x, const float* __restrict__ dy, const 
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
 #pragma unroll
-        for (int a = 0; a < WG_CIB; ++a) {
+        for (int a = 0; a < CIB; ++a) {
             float v = acc[a][q];
             for (int off = 16; off >= LPG; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
             if (g == 0) red[warp][a][cq] = v;
         }
         __syncthreads();
-        for (int idx = threadIdx.x; idx < WG_CIB * 32; idx += blockDim.x) {
+        for (int idx = threadIdx.x; idx < CIB * 32; idx += blockDim.x) {
             const int a = idx >> 5, c = idx & 31, co = 4 * c + q;
             if (ci0 + a >= Cin || co >= Cout || c >= LPG) continue;
             float v = 0.0f;
@@ -111,7 +112,8 @@ __global__ void k_wgrad_reduce(const float* __restrict__ partial, int S, int64_t
 
 extern "C" int32_t insmos_sparse_conv_wgrad_slices(int64_t n_out, int32_t TM, int32_t K, int32_t Cin) {
     const int64_t n_tiles = ceil_div64(n_out > 0 ? n_out : 1, TM);
-    const int nz = (Cin + WG_CIB - 1) / WG_CIB;
+    const int cib = Cin <= 4 ? 4 : (Cin <= 8 ? 8 : WG_CIB);
+    const int nz = (Cin + cib - 1) / cib;
     int64_t S = ceil_div64(1184, (int64_t)K * nz);                     // ~8 blocks per SM
     if (S > 64) S = 64;
     if (S > n_tiles) S = n_tiles;
@@ -136,9 +138,12 @@ extern "C" int insmos_sparse_conv_wgrad(const float* in, int64_t n_in, int32_t C
     int LPG = 1;                                                          // lanes per row: next power of two >= ceil(Cout / 4)
     while (LPG * 4 < Cout) LPG <<= 1;
     const int64_t n_tiles = ceil_div64(n_out, TM);
-    const dim3 grid((unsigned)K, (unsigned)S, (unsigned)((Cin + WG_CIB - 1) / WG_CIB));
+    const int cib = Cin <= 4 ? 4 : (Cin <= 8 ? 8 : WG_CIB);
+    const dim3 grid((unsigned)K, (unsigned)S, (unsigned)((Cin + cib - 1) / cib));
     const int aligned = ((reinterpret_cast<uintptr_t>(in) & 15) == 0 ? 1 : 0) | ((reinterpret_cast<uintptr_t>(dout) & 15) == 0 ? 2 : 0);
-    k_spconv_wgrad<2><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, LPG, n_tiles, S, aligned, partial);
+    if (cib == 4) k_spconv_wgrad<4, 4><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, LPG, n_tiles, S, aligned, partial);
+    else if (cib == 8) k_spconv_wgrad<4, 8><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, LPG, n_tiles, S, aligned, partial);
+    else k_spconv_wgrad<2, WG_CIB><<<grid, WG_WARPS * 32, 0, st>>>(in, dout, seg, entries, TM, K, Cin, Cout, LPG, n_tiles, S, aligned, partial);
     INSMOS_CHECK_LAUNCH("k_spconv_wgrad");
     k_wgrad_reduce<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(partial, S, n, dweight);
     INSMOS_CHECK_LAUNCH("k_wgrad_reduce");
