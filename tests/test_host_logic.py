@@ -54,3 +54,53 @@ def test_product_refuses_cpu_tensors_and_cpu_models():
         ops.voxelize4d(torch.zeros((4, 5)), [0.1, 0.1, 0.1, 0.1])
     with pytest.raises(RuntimeError, match="CUDA"):
         pipeline.ScanPipeline(torch.nn.Linear(2, 2), n_scans=2, max_points=16)
+
+
+# ---- training step host logic (N3): flat buffers, StepLR schedule, refusal of the CUDA-only pieces on CPU ------------------
+def test_flat_parameters_are_views_of_one_buffer_and_gradients_accumulate_in_place():
+    import torch
+    from insmos_b200.train import FlatParameters, TrainStep
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.BatchNorm1d(3), torch.nn.Linear(3, 2))
+    before = [p.detach().clone() for p in net.parameters()]
+    flat = FlatParameters(net)
+    assert flat.numel == sum(p.numel() for p in net.parameters())
+    o = 0
+    for p, b in zip(net.parameters(), before):
+        assert torch.equal(p.detach(), b)                                   # values preserved
+        assert p.data_ptr() == flat.data.data_ptr() + 4 * o and p.grad.data_ptr() == flat.grad.data_ptr() + 4 * o
+        o += p.numel()
+    net(torch.randn(8, 4)).sum().backward()
+    g1 = flat.grad.clone()
+    assert float(g1.abs().sum()) > 0
+    net(torch.randn(8, 4)).sum().backward()                                 # autograd accumulates INTO the flat buffer
+    assert not torch.equal(flat.grad, g1)
+    net.zero_grad(set_to_none=True)                                         # a caller that drops .grad: re-attached by zero_grad()
+    flat.zero_grad()
+    assert all(p.grad is not None and p.grad.data_ptr() >= flat.grad.data_ptr() for p in net.parameters())
+    assert float(flat.grad.abs().sum()) == 0.0
+    ts = TrainStep.__new__(TrainStep)
+    ts.base_lr, ts.lr_decay, ts.lr_epoch, ts.epoch = 1e-4, 0.99, 1, 0
+    assert ts.lr == 1e-4
+    ts.set_epoch(10)
+    assert abs(ts.lr - 1e-4 * 0.99 ** 10) < 1e-18                           # StepLR(step_size=1, gamma=0.99), models.py:187-189
+    ts.lr_epoch = 4
+    assert abs(ts.lr - 1e-4 * 0.99 ** 2) < 1e-18
+
+
+def test_training_kernels_refuse_cpu_tensors():
+    import pytest
+    import torch
+    from insmos_b200 import autograd, ops
+    x = torch.randn(16, 4, requires_grad=True)
+    assert autograd.needs_grad(x) and not autograd.needs_grad(x.detach(), None)
+    with torch.no_grad():
+        assert not autograd.needs_grad(x)
+    with pytest.raises(RuntimeError):
+        autograd.batch_norm_train(torch.nn.BatchNorm1d(4), x)
+    with pytest.raises(RuntimeError):
+        autograd.gather_rows(x, torch.zeros(3, dtype=torch.int32))
+    with pytest.raises((RuntimeError, ValueError)):
+        ops.adam_step(torch.zeros(4), torch.zeros(4), torch.zeros(4), torch.zeros(4), 1e-3, 0.9, 0.999, 1e-8, 0.0, 1)
+    with pytest.raises(RuntimeError):
+        ops.center_targets(torch.zeros((1, 8)), 100, 250, 300, 3, -60, -50, 0.1, 0.1, 4, 0.1, 2)
