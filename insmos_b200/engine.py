@@ -4,7 +4,7 @@ Why.  One forward is ~180 kernel launches with ~11 small device->host reads of d
 level, candidate count); each read drains the stream and the GPU idles until the host has queued the next kernels
 (measured: 7.0 ms per step for 6.2 ms of kernels), and many of the kernels on the coarse levels do not
 fill 148 SMs.  Samples are independent (models/models.py:313 processes them one by one), so two or three forwards in
-flight on separate streams fill each other's bubbles: the C ABI releases the GIL inside every call (ctypes.CDLL) and the
+flight on separate streams fill each other's bubbles: the C-ABI calls only queue kernels (and keep the GIL: PyDLL, see _lib.load) and the
 reads block outside the GIL.  Streams and threads instead of a static-shape graph capture: every sample has its own shapes.
 """
 import queue
