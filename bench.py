@@ -423,7 +423,11 @@ def main():
     from insmos_b200.distributed import gather_logits_padded
 
     n_clouds = 4
-    host = [torch.from_numpy(c).pin_memory() for c in make_clouds(rank, n_clouds)]
+    # weak scaling = the SAME work on every GPU: all ranks draw from the same four clouds (seeds 0-3), each rank starting at
+    # a different one.  (Per-rank seeds made the ranks' work unequal: the synthetic clouds hold 296 k - 506 k 4D voxels, the
+    # four-cloud mean of a rank ranged 398 k - 443 k, and a K-step region ends with the slowest rank.)
+    host = [torch.from_numpy(c).pin_memory() for c in make_clouds(0, n_clouds)]
+    host = host[rank % n_clouds:] + host[:rank % n_clouds]
     dev = [h.to(device) for h in host]
     net = build_model(device)
     gather_out = torch.empty((world, GATHER_PAD_ROWS + 1, 3), dtype=torch.float32, device=device) if world > 1 else None
@@ -623,6 +627,7 @@ def main():
                        "arithmetic": "fp32; sparse-conv products on tensor cores as 3xTF32 (fp32-accurate) or fp32 FFMA; cuDNN TF32 off",
                        "weights": "tests/golden/insmos_c2.npz (the C2 parity golden's weights)",
                        "streams": args.streams, "cpus_bound_per_rank": bound,
+                       "clouds": "every rank processes the same %d synthetic clouds (seeds 0-%d), rotated by rank: identical work per GPU" % (n_clouds, n_clouds - 1),
                        "points_per_step": int(dev[0].shape[0]), "current_points": n_cur},
             "timing": {"regions": len(regions), "steps_per_region": args.steps, "timed_s": round(sum(regions) / 1000.0, 3),
                        "ms_per_step_median": round(ms / args.steps, 4), "ms_per_step_min": round(min(regions) / args.steps, 4),
