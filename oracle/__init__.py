@@ -13,7 +13,9 @@ What it restates (paths relative to the reference repository, nubot-nudt/InsMOS)
 * ``oracle/sp.py``      spconv 2.3.6 semantics used by models/backbones_3d/voxel_generate.py:17-31 and
                         models/backbones_3d/spconv_unet.py:120-410 (PointToVoxel.generate_voxel_with_id,
                         SubM / strided / inverse convolution with indice_key reuse, dense(), gather by id).
-* ``oracle/native/oracle_native.c``  rotated-BEV IoU + NMS (models/bbox_post_process/src/iou3d_nms_kernel.cu:15-311,
+* ``oracle/native/oracle_native.c``  kernel-map neighbour table (hash map of the input coordinates, kernel offsets probed in
+                        parallel with OpenMP -- how the two libraries' CPU backends build their maps; checked against the
+                        numpy statement in me.py / sp.py), rotated-BEV IoU + NMS (models/bbox_post_process/src/iou3d_nms_kernel.cu:15-311,
                         host twin iou3d_cpu.cpp:38-228, sweep iou3d_nms.cpp:90-136) and
                         Array_Index.find_features_by_bbox_with_yaw (models/utils/src/Array_Index.cpp:14-79).
 * ``oracle/graph.py``   the model graph models/models.py:297-376 + the modules it calls, as one

@@ -111,15 +111,35 @@ class Lookup:
 
     def find(self, coords):
         k = pack_keys(coords)
-        pos = np.searchsorted(self.sorted, k)
-        pos = np.minimum(pos, len(self.sorted) - 1) if len(self.sorted) else pos
-        hit = (self.sorted[pos] == k) if len(self.sorted) else np.zeros(len(k), dtype=bool)
-        return np.where(hit, self.order[pos], -1)
+        if len(self.sorted) == 0:                      # empty input set: nothing can be found
+            return np.full(len(k), -1, dtype=np.int64)
+        pos = np.minimum(np.searchsorted(self.sorted, k), len(self.sorted) - 1)
+        return np.where(self.sorted[pos] == k, self.order[pos], -1)
 
 
-def kernel_map(in_coords, out_coords, ksize, in_stride):
+# Above this many (row, offset) probes the neighbour lookups of a kernel map run in oracle/native (hash map + OpenMP over the
+# offsets -- how ME's and spconv's CPU backends do it); below it, and always with native=False, the plain numpy statement
+# (stable sort + binary search).  Both give the same maps in the same order: tests/test_oracle_ops.py.
+NATIVE_MIN_PROBES = 1 << 18
+
+
+def maps_from_neighbor_table(nbr):
+    """[K, n_out] table of input rows (-1 = absent) -> [(in_idx, out_idx)] per offset, output rows ascending."""
+    maps = []
+    for k in range(nbr.shape[0]):
+        o = np.nonzero(nbr[k] >= 0)[0]
+        maps.append((nbr[k][o].astype(np.int64), o))
+    return maps
+
+
+def kernel_map(in_coords, out_coords, ksize, in_stride, native=None):
     """[(in_idx, out_idx)] per offset k:  in = out + offset_k  (covers stride-1 and strided convs)."""
     offs = kernel_offsets(ksize, in_stride)
+    if native is None:
+        native = len(out_coords) * len(offs) >= NATIVE_MIN_PROBES and np.asarray(in_coords).shape[1] in (4, 5)
+    if native:
+        from . import native as _native
+        return maps_from_neighbor_table(_native.neighbor_table(in_coords, out_coords, offs))
     lut = Lookup(in_coords)
     oc = np.asarray(out_coords).astype(np.int64)
     maps = []

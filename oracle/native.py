@@ -28,8 +28,27 @@ def lib():
         L.oracle_find_point_in_instance_bbox_with_yaw.restype = None
         L.oracle_find_point_in_instance_bbox_with_yaw.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                                                   C.c_int, C.c_float]
+        L.oracle_neighbor_table.restype = C.c_int
+        L.oracle_neighbor_table.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                            C.c_void_p]
         _lib = L
     return _lib
+
+
+def neighbor_table(in_coords, q_coords, offs):
+    """rows of `q + offs[k]` in in_coords for every kernel offset k: int32 [K, n_q], -1 = absent (hash map + OpenMP over the
+    offsets; the numpy statement it must equal is oracle/me.py::kernel_map / oracle/sp.py::subm_maps with native=False)."""
+    a = np.ascontiguousarray(in_coords, dtype=np.int64)
+    q = np.ascontiguousarray(q_coords, dtype=np.int64)
+    o = np.ascontiguousarray(offs, dtype=np.int64)
+    if a.ndim != 2 or q.ndim != 2 or a.shape[1] != q.shape[1] or o.ndim != 2:
+        raise ValueError("neighbor_table: [n,ncol] coordinate rows and [K,D] offsets expected")
+    nbr = np.empty((o.shape[0], q.shape[0]), dtype=np.int32)
+    rc = lib().oracle_neighbor_table(a.ctypes.data, a.shape[0], q.ctypes.data, q.shape[0], a.shape[1], o.ctypes.data, o.shape[0],
+                                     o.shape[1], nbr.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("oracle_neighbor_table failed (%d)" % rc)
+    return nbr
 
 
 def overlap_matrix(a, b):

@@ -113,6 +113,8 @@ void oracle_iou_matrix(const float* a, int na, const float* b, int nb, float* ou
 int oracle_nms(const float* boxes, int n, float thresh, int64_t* keep) {
     const int cb = (n + 63) / 64;
     uint64_t* mask = (uint64_t*)calloc((size_t)n * cb + 1, sizeof(uint64_t));
+    /* every 64-bit mask word is independent (the reference computes them in parallel CUDA blocks): rows in parallel */
+#pragma omp parallel for schedule(dynamic, 8)
     for (int i = 0; i < n; ++i)                           /* nms_kernel :267-311 */
         for (int c = i / 64; c < cb; ++c) {
             uint64_t t = 0;
@@ -195,4 +197,74 @@ void oracle_find_point_in_instance_bbox_with_yaw(const float* pts, int n, int st
             }
         }
     }
+}
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Kernel-map neighbour table (MinkowskiEngine CPU coordinate map / spconv CPU indice pairs, restated: both libraries keep
+ * the input coordinates in a hash map and, for every kernel offset, probe `query + offset` for every query row; ME runs the
+ * offsets in parallel with OpenMP).  Same result as oracle/me.py::kernel_map / oracle/sp.py::subm_maps, which remain the
+ * plain-numpy statement (sort + binary search) and the checker of this function (tests/test_oracle_ops.py).
+ *
+ *   in_coords  [n_in, ncol]  int64 rows (batch, c0, c1, c2[, c3]); duplicates: the FIRST row wins (as np.searchsorted on a
+ *                            stable sort does)
+ *   q_coords   [n_q, ncol]   query rows
+ *   offs       [K, D]        per-offset deltas, added to columns 1 .. D
+ *   nbr        [K, n_q]      out: row of `q + offs[k]` in in_coords, or -1 (also -1 when the shifted coordinate leaves the
+ *                            packable range |c0..c2| < 2^15, |c3| < 128 -- oracle/me.py::kernel_map's `ok` mask)
+ * Key packing = oracle/me.py::pack_keys. */
+
+static inline uint64_t okm_mix(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+static inline int64_t okm_pack(int64_t b, int64_t c0, int64_t c1, int64_t c2, int64_t c3) {
+    const int64_t B = 1 << 15;
+    int64_t key = b;
+    key = key * (2 * B) + (c0 + B);
+    key = key * (2 * B) + (c1 + B);
+    key = key * (2 * B) + (c2 + B);
+    return key * 256 + (c3 + 128);
+}
+
+int oracle_neighbor_table(const int64_t* in_coords, int64_t n_in, const int64_t* q_coords, int64_t n_q, int ncol,
+                          const int64_t* offs, int K, int D, int32_t* nbr) {
+    if (ncol < 4 || ncol > 5 || D < 1 || D > ncol - 1 || n_in < 0 || n_q < 0 || K < 0 || n_in > 0x7fffffffLL) return -1;
+    uint64_t cap = 16;
+    while (cap < 2 * (uint64_t)n_in) cap <<= 1;
+    const uint64_t mask = cap - 1;
+    int64_t* keys = (int64_t*)malloc(cap * sizeof(int64_t));
+    int32_t* rows = (int32_t*)malloc(cap * sizeof(int32_t));
+    if (!keys || !rows) { free(keys); free(rows); return -2; }
+    for (uint64_t i = 0; i < cap; ++i) keys[i] = -1;                       /* packed keys of valid rows are >= 0 */
+    for (int64_t i = 0; i < n_in; ++i) {                                    /* sequential insert: the first row of a key wins */
+        const int64_t* c = in_coords + i * ncol;
+        const int64_t key = okm_pack(c[0], c[1], c[2], c[3], ncol > 4 ? c[4] : 0);
+        uint64_t s = okm_mix((uint64_t)key) & mask;
+        while (keys[s] != -1 && keys[s] != key) s = (s + 1) & mask;
+        if (keys[s] == -1) { keys[s] = key; rows[s] = (int32_t)i; }
+    }
+    const int64_t B = 1 << 15;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int k = 0; k < K; ++k) {
+        int64_t d[4] = {0, 0, 0, 0};
+        for (int j = 0; j < D; ++j) d[j] = offs[(int64_t)k * D + j];
+        int32_t* out = nbr + (int64_t)k * n_q;
+        for (int64_t i = 0; i < n_q; ++i) {
+            const int64_t* c = q_coords + i * ncol;
+            const int64_t c0 = c[1] + d[0], c1 = c[2] + d[1], c2 = c[3] + d[2], c3 = (ncol > 4 ? c[4] : 0) + d[3];
+            int32_t r = -1;
+            if (c0 > -B && c0 < B && c1 > -B && c1 < B && c2 > -B && c2 < B && (ncol <= 4 || (c3 > -128 && c3 < 128))) {
+                const int64_t key = okm_pack(c[0], c0, c1, c2, c3);
+                uint64_t s = okm_mix((uint64_t)key) & mask;
+                while (keys[s] != -1) {
+                    if (keys[s] == key) { r = rows[s]; break; }
+                    s = (s + 1) & mask;
+                }
+            }
+            out[i] = r;
+        }
+    }
+    free(keys);
+    free(rows);
+    return 0;
 }

@@ -71,11 +71,17 @@ def _offsets3(ksize):
     return o
 
 
-def subm_maps(indices, ksize):
-    """SubMConv3d pairs: in = out + (k - ksize//2).  indices [N,4] (b,z,y,x)."""
+def subm_maps(indices, ksize, native=None):
+    """SubMConv3d pairs: in = out + (k - ksize//2).  indices [N,4] (b,z,y,x).  Large maps look their neighbours up in
+    oracle/native (hash map, OpenMP over the offsets); native=False is the numpy statement both must equal."""
     ind = np.asarray(indices).astype(np.int64)
-    lut = me.Lookup(ind)
     offs = _offsets3(ksize) - np.asarray([k // 2 for k in ksize])[None, :]
+    if native is None:
+        native = len(ind) * len(offs) >= me.NATIVE_MIN_PROBES
+    if native:
+        from . import native as _native
+        return me.maps_from_neighbor_table(_native.neighbor_table(ind, ind, offs))
+    lut = me.Lookup(ind)
     maps = []
     for k in range(len(offs)):
         q = ind.copy()

@@ -208,3 +208,43 @@ def test_spconv_subm_strided_inverse_match_dense():
         chain.append(s)
     chain.append(sp.conv_out_shape(s, [3, 1, 1], [2, 1, 1], [0, 0, 0]))
     assert chain == [[41, 1000, 1200], [21, 500, 600], [11, 250, 300], [6, 125, 150], [2, 125, 150]]
+
+
+def _same_maps(a, b):
+    assert len(a) == len(b)
+    for (i1, o1), (i2, o2) in zip(a, b):
+        assert i1.dtype == i2.dtype == np.int64
+        assert np.array_equal(i1, i2) and np.array_equal(o1, o2)
+
+
+def test_native_neighbor_table_equals_the_numpy_statement():
+    """large kernel maps are looked up in oracle/native (hash map + OpenMP over the offsets); the numpy statement (stable sort +
+    binary search) is its checker: same pairs in the same order, incl. duplicated input rows (first row wins), coordinates at
+    the edge of the packable range, strided maps, even kernels, empty sets, and the brute-force loop on a small 4D set."""
+    rng = np.random.default_rng(11)
+    for trial in range(4):
+        n = 2500
+        c = np.concatenate([np.zeros((n, 1), int), rng.integers(-6, 7, (n, 3)), rng.integers(-3, 1, (n, 1))], 1)
+        if trial % 2:
+            c[:50, 1] = 32767; c[50:100, 2] = -32767; c[100:120, 4] = 127; c[120:140, 4] = -127
+        if trial == 2:
+            c = np.concatenate([c, c[:400]], 0)
+        out = c[rng.permutation(len(c))[:1500]]
+        for ks, st in (([3, 3, 3, 3], [1, 1, 1, 1]), ([2, 2, 2, 1], [1, 1, 1, 1]), ([5, 5, 5, 1], [1, 1, 1, 1]), ([3, 3, 3, 3], [2, 2, 2, 1])):
+            _same_maps(me.kernel_map(c, out, ks, st, native=False), me.kernel_map(c, out, ks, st, native=True))
+    e = np.zeros((0, 5), int)
+    for a, b in ((e, e), (c, e), (e, c)):
+        _same_maps(me.kernel_map(a, b, [3, 3, 3, 3], [1, 1, 1, 1], native=False), me.kernel_map(a, b, [3, 3, 3, 3], [1, 1, 1, 1], native=True))
+    ind = _rand_coords3(rng, 4000, 20).astype(np.int64)
+    _same_maps(sp.subm_maps(ind, (3, 3, 3), native=False), sp.subm_maps(ind, (3, 3, 3), native=True))
+    ind[:10, 3] = 32767
+    _same_maps(sp.subm_maps(ind, (3, 3, 3), native=False), sp.subm_maps(ind, (3, 3, 3), native=True))
+    # brute force, through the native path
+    c = _rand_coords3(rng, 120, 6, ncol=5)
+    maps = me.kernel_map(c, c, [3, 3, 3, 3], [1, 1, 1, 1], native=True)
+    lut = {tuple(r): i for i, r in enumerate(c)}
+    brute = sorted((k, lut[q], o) for k, off in enumerate(me.kernel_offsets([3, 3, 3, 3], [1, 1, 1, 1])) for o, r in enumerate(c)
+                   for q in [(r[0], r[1] + off[0], r[2] + off[1], r[3] + off[2], r[4] + off[3])] if q in lut)
+    assert brute == [tuple(t) for t in me.maps_to_triples(maps, len(c), len(c))]
+    # the automatic switch takes the native path only for large maps
+    assert 120 * 81 < me.NATIVE_MIN_PROBES
