@@ -181,7 +181,7 @@ def cpu_port_full(sd_cpu, budget_s, max_steps, warmup=0):
     dt = float(np.mean(times))
     return {"value": 1.0 / dt, "unit": "scans/s", "cores": torch.get_num_threads(), "host_cores": os.cpu_count(), "kind": "port",
             "sample": "the full C2 cloud (10 scans x 64 x 1875 rays = 1.2 M points, seed 0), %d forward(s) of oracle/graph.py, "
-                      "%.1f s each, no extrapolation; BLAS = torch MKL" % (len(times), dt),
+                      "%.1f s each, no extrapolation; BLAS = torch MKL, kernel-map lookups = oracle/native (hash map, OpenMP)" % (len(times), dt),
             "steps": len(times), "warmup_steps": warm_done, "seconds_per_step": dt,
             "rulebook_s": timing.get("me_maps_s"), "me_conv_s": timing.get("me_conv_s"), "motionnet_s": timing.get("motionnet_s"),
             "unet_encoder_s": timing.get("unet_encoder_s"), "bev_s": timing.get("bev_s"), "decoder_s": timing.get("decoder_s")}
