@@ -162,6 +162,8 @@ def cpu_port_full(sd_cpu, budget_s, max_steps, warmup=0):
     # the port's hot loops are small MKL GEMMs + index_add; beyond ~16 threads they get slower (measured on the
     # 128-core GPU host: 128 threads -> 30x slower than 16), so "all the threads it can use" is capped at 16
     torch.set_num_threads(min(os.cpu_count() or 1, 16))
+    from oracle import native as oracle_native
+    oracle_native.set_threads(torch.get_num_threads())        # torchrun exports OMP_NUM_THREADS=1: the native loops get the same count
     pts = make_clouds(0, 1)[0]
     times, timing = [], {}
     warm_done, t_begin = 0, time.perf_counter()

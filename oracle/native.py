@@ -35,6 +35,17 @@ def lib():
     return _lib
 
 
+def set_threads(n):
+    """threads of the OpenMP loops in liboracle_native.so (kernel-map lookups, NMS mask rows); returns the count in effect."""
+    L = lib()
+    L.oracle_set_threads.restype = None
+    L.oracle_set_threads.argtypes = [C.c_int]
+    L.oracle_max_threads.restype = C.c_int
+    L.oracle_max_threads.argtypes = []
+    L.oracle_set_threads(int(n))
+    return int(L.oracle_max_threads())
+
+
 def neighbor_table(in_coords, q_coords, offs):
     """rows of `q + offs[k]` in in_coords for every kernel offset k: int32 [K, n_q], -1 = absent (hash map + OpenMP over the
     offsets; the numpy statement it must equal is oracle/me.py::kernel_map / oracle/sp.py::subm_maps with native=False)."""

@@ -213,6 +213,25 @@ void oracle_find_point_in_instance_bbox_with_yaw(const float* pts, int n, int st
  *                            packable range |c0..c2| < 2^15, |c3| < 128 -- oracle/me.py::kernel_map's `ok` mask)
  * Key packing = oracle/me.py::pack_keys. */
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+/* threads of the parallel loops below (torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU baseline sets its own count) */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+int oracle_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
 static inline uint64_t okm_mix(uint64_t x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
     return x;
