@@ -104,3 +104,28 @@ def test_training_kernels_refuse_cpu_tensors():
         ops.adam_step(torch.zeros(4), torch.zeros(4), torch.zeros(4), torch.zeros(4), 1e-3, 0.9, 0.999, 1e-8, 0.0, 1)
     with pytest.raises(RuntimeError):
         ops.center_targets(torch.zeros((1, 8)), 100, 250, 300, 3, -60, -50, 0.1, 0.1, 4, 0.1, 2)
+
+
+def test_reference_arm_prints_one_contract_line(tmp_path):
+    """`bench.py --impl reference` needs no GPU: it times the CPU port on the FULL C2 cloud and prints exactly one JSON line
+    with the contract's keys, the counts of steps actually run, and the rule-book / convolution split."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, INSMOS_REF_BUDGET_S="1", OMP_NUM_THREADS="1")         # one timed step; torchrun-like OMP setting
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "0"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "scans_per_sec" and d["unit"] == "scans/s" and d["higher_is_better"] is True
+    assert d["steps"] == 1 and d["warmup"] == 0 and d["requested"] == {"steps": 3, "warmup": 0}
+    assert d["value"] > 0 and abs(d["value"] - 1000.0 / d["ms_per_step"]) < 1e-9
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["cores"] >= 1 and cb["steps"] == 1
+    assert cb["rulebook_s"] > 0 and cb["me_conv_s"] > 0 and "no extrapolation" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "C2" in d["config"]["workload"]
