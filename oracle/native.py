@@ -113,10 +113,34 @@ def _load_ext(name, path):
     return mod
 
 
+class _KeepThreadCount:
+    """proxy of the reference's Array_Index module.  Its functions call omp_set_num_threads(30) (Array_Index.cpp:19,88) and leave
+    the process-wide OpenMP thread count there, which oversubscribes every later torch CPU operation of the process (measured
+    here: the training-oracle fixture 3 s -> 36 s on 8 cores).  The proxy restores the count after each call."""
+
+    def __init__(self, mod):
+        self._mod = mod
+
+    def __getattr__(self, name):
+        fn = getattr(self._mod, name)
+        if not callable(fn):
+            return fn
+
+        def call(*args, **kwargs):
+            import torch
+            n = torch.get_num_threads()
+            try:
+                return fn(*args, **kwargs)
+            finally:
+                torch.set_num_threads(n)
+                set_threads(n)
+        return call
+
+
 def ref_array_index():
     """the reference's compiled Array_Index module (oracle/_ref), or None."""
     p = build.ref_paths()[0]
-    return _load_ext("Array_Index", p) if os.path.exists(p) else None
+    return _KeepThreadCount(_load_ext("Array_Index", p)) if os.path.exists(p) else None
 
 
 def ref_iou3d():
