@@ -248,3 +248,34 @@ def test_native_neighbor_table_equals_the_numpy_statement():
     assert brute == [tuple(t) for t in me.maps_to_triples(maps, len(c), len(c))]
     # the automatic switch takes the native path only for large maps
     assert 120 * 81 < me.NATIVE_MIN_PROBES
+
+
+def test_c4_size_sets_and_maps_equal_the_stored_digests():
+    """BASELINE config 4 scale (3 M points, voxel 0.05 m: 1.4 M voxels, maps of 1.4-25.7 M pairs): the oracle with native kernel-map
+    lookups reproduces tests/golden/maps_c4.json, which was written through the numpy statement (make_golden_c2.py --c4-only).
+    These are the digests the CUDA rule books are compared with on the GPU (tests/test_gpu_c2_golden.py::test_c4_size_maps_bit_exact)."""
+    import hashlib
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import golden_util
+    from insmos_b200 import synth
+    want = json.load(open(os.path.join(golden_util.GOLDEN_DIR, "maps_c4.json")))
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()          # noqa: E731
+    pts = synth.make_sequence(**want["synth"])
+    assert len(pts) == want["n_points"]
+    coords, _ = me.quantize_points(np.concatenate([pts[:, 0:3], pts[:, 4:5]], axis=1), [want["voxel"]] * 3 + [0.1])
+    uniq, inv = me.unique_first(coords)
+    assert {"n": int(len(uniq)), "sha": sha(uniq.astype(np.int32))} == want["sets"]["ts1"]
+    assert sha(inv.astype(np.int32)) == want["inverse_sha"]
+    c2, _ = me.stride_coords(uniq, [2, 2, 2, 1])
+    assert {"n": int(len(c2)), "sha": sha(c2.astype(np.int32))} == want["sets"]["ts2"]
+    for name, (ic, oc, ks, st) in {"ts1_5x5x5x1": (uniq, uniq, [5, 5, 5, 1], [1, 1, 1, 1]),
+                                   "ts1_3x3x3x3": (uniq, uniq, [3, 3, 3, 3], [1, 1, 1, 1]),
+                                   "ts1_to_ts2_2x2x2x1": (uniq, c2, [2, 2, 2, 1], [1, 1, 1, 1]),
+                                   "ts2_3x3x3x3": (c2, c2, [3, 3, 3, 3], [2, 2, 2, 1])}.items():
+        maps = me.kernel_map(ic, oc, ks, st, native=True)
+        ks_ = np.concatenate([np.full(len(i), k, dtype=np.int64) for k, (i, o) in enumerate(maps)])
+        s, x = golden_util.triple_digest(ks_, np.concatenate([i for i, o in maps]), np.concatenate([o for i, o in maps]))
+        assert {"pairs": int(len(ks_)), "sum": s, "xor": x, "n_in": int(len(ic)), "n_out": int(len(oc))} == want["maps"][name], name
