@@ -41,6 +41,11 @@ class StreamWorkers:
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.n)]
         self.threads = [threading.Thread(target=self._loop, args=(i,), daemon=True) for i in range(self.n)]
         self._next = 0
+        # Cold start: the first job fills the per-layer caches (prepared weight images, folded BatchNorm constants) with
+        # kernels queued on ITS stream; a second job on another stream would find the cache entries and could read them before
+        # those kernels have run.  Until one job has completed on the device the jobs therefore run one at a time.
+        self._primed = False
+        self._prime_lock = threading.Lock()
         for t in self.threads:
             t.start()
 
@@ -51,6 +56,9 @@ class StreamWorkers:
             job = self.queues[i].get()
             if job is None:
                 return
+            cold = not self._primed
+            if cold:
+                self._prime_lock.acquire()
             try:
                 with torch.cuda.stream(stream), torch.no_grad():
                     if job.ready is not None:
@@ -58,8 +66,14 @@ class StreamWorkers:
                     job.result = job.fn(*job.args)
                     job.done_event = torch.cuda.Event()
                     job.done_event.record(stream)
+                    if cold and not self._primed:
+                        stream.synchronize()                         # what this job cached is now complete on the device
+                        self._primed = True
             except BaseException as e:                               # surfaced by wait()
                 job.error = e
+            finally:
+                if cold:
+                    self._prime_lock.release()
             job.finished.set()
 
     def submit(self, fn, *args, worker=None):

@@ -129,3 +129,65 @@ def test_reference_arm_prints_one_contract_line(tmp_path):
     assert cb["rulebook_s"] > 0 and cb["me_conv_s"] > 0 and "no extrapolation" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "C2" in d["config"]["workload"]
+
+
+def test_stream_workers_serialise_the_cold_start_then_run_concurrently(monkeypatch):
+    """engine.StreamWorkers control flow on fake CUDA objects: until one job has completed on the device (stream.synchronize
+    after the first successful job) the jobs run one at a time -- the first forward fills the per-layer weight caches on its own
+    stream --, afterwards the workers overlap; a failing first job is surfaced by wait() and does not prime the pool."""
+    import contextlib
+    import threading
+    import time
+    from insmos_b200 import engine
+
+    class FakeStream:
+        def __init__(self, device=None):
+            self.syncs = 0
+
+        def wait_event(self, ev):
+            pass
+
+        def synchronize(self):
+            self.syncs += 1
+
+    class FakeEvent:
+        def __init__(self, enable_timing=False):
+            pass
+
+        def record(self, stream=None):
+            pass
+
+    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: FakeStream())
+    log, lock = [], threading.Lock()
+
+    def work(tag, fail=False):
+        t0 = time.perf_counter()
+        time.sleep(0.08)
+        if fail:
+            raise ValueError("boom %s" % tag)
+        with lock:
+            log.append((tag, t0, time.perf_counter()))
+        return tag
+
+    pool = engine.StreamWorkers("cuda:0", workers=2)
+    try:
+        bad = pool.submit(work, "bad", True)                     # first job fails: surfaced, pool stays cold
+        with pytest.raises(ValueError):
+            bad.wait(FakeStream())
+        assert not pool._primed and sum(s.syncs for s in pool.streams) == 0
+        a, b = pool.submit(work, "a"), pool.submit(work, "b")   # cold: one at a time, exactly one priming synchronize
+        assert {a.wait(FakeStream()), b.wait(FakeStream())} == {"a", "b"}
+        assert pool._primed and sum(s.syncs for s in pool.streams) == 1
+        iv = {t: (s, e) for t, s, e in log}
+        assert iv["a"][1] <= iv["b"][0] or iv["b"][1] <= iv["a"][0]            # no overlap
+        c, d = pool.submit(work, "c"), pool.submit(work, "d")   # primed: the two workers overlap
+        c.wait(FakeStream()); d.wait(FakeStream())
+        iv = {t: (s, e) for t, s, e in log}
+        assert iv["c"][0] < iv["d"][1] and iv["d"][0] < iv["c"][1]
+        assert sum(s.syncs for s in pool.streams) == 1
+    finally:
+        pool.close()
